@@ -1,0 +1,171 @@
+"""ctypes binding of liboracle.so -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  Nothing under izpi_b200/ may.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from izpi_b200.scene import NODE_DTYPE, SceneSpec, SceneSpecC
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_DIR, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the C++ restatement (g++ is in the image; takes a few seconds)."""
+    srcs = [os.path.join(_DIR, f) for f in os.listdir(_DIR) if f.endswith((".cpp", ".hpp", ".h"))]
+    srcs.append(os.path.join(_DIR, "..", "include", "izpi_scene.h"))
+    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", _DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("nodes", "tris", "spheres", "others", "rays")]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
+                ("sampler", C.c_int32), ("rng_mode", C.c_int32), ("flavour", C.c_int32), ("threads", C.c_int32),
+                ("seed", C.c_uint64), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
+                ("epilogue", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.oracle_ray_aabb4.restype = C.c_uint8
+        L.oracle_ray_aabb4.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
+        L.oracle_conservative_float32_min.restype = C.c_float
+        L.oracle_conservative_float32_min.argtypes = [C.c_double]
+        L.oracle_conservative_float32_max.restype = C.c_float
+        L.oracle_conservative_float32_max.argtypes = [C.c_double]
+        L.oracle_lcg_next.restype = C.c_double
+        L.oracle_lcg_next.argtypes = [C.POINTER(C.c_uint64)]
+        L.oracle_sample_wavelength.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.oracle_cie_values.argtypes = [C.c_double, C.c_void_p]
+        L.oracle_scene_create.restype = C.c_void_p
+        L.oracle_scene_create.argtypes = [C.POINTER(SceneSpecC)]
+        L.oracle_scene_destroy.argtypes = [C.c_void_p]
+        L.oracle_scene_num_nodes.restype = C.c_int32
+        L.oracle_scene_num_nodes.argtypes = [C.c_void_p]
+        L.oracle_scene_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_scene_num_lights.restype = C.c_int32
+        L.oracle_scene_num_lights.argtypes = [C.c_void_p]
+        L.oracle_scene_lights.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_prim_bbox.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.oracle_triangle_fields.restype = C.c_int
+        L.oracle_triangle_fields.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.oracle_spectral_texture_value.restype = C.c_double
+        L.oracle_spectral_texture_value.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+        L.oracle_hit.restype = C.c_int32
+        L.oracle_hit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.oracle_trace.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                   C.c_void_p, C.c_void_p, C.POINTER(Stats), C.c_int]
+        L.oracle_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_firefly_rejection.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.oracle_xyz_to_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double]
+        L.oracle_tiles.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        _lib = L
+    return _lib
+
+
+def ray_aabb4(flavour, org, inv, bounds, tmax) -> int:
+    o = np.ascontiguousarray(org, dtype=np.float32)
+    i = np.ascontiguousarray(inv, dtype=np.float32)
+    b = np.ascontiguousarray(bounds, dtype=np.float32).reshape(24)
+    return int(lib().oracle_ray_aabb4(flavour, o.ctypes.data, i.ctypes.data, b.ctypes.data, np.float32(tmax)))
+
+
+def tiles(sx, sy):
+    a, b = C.c_int32(), C.c_int32()
+    lib().oracle_tiles(sx, sy, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+class OracleScene:
+    """The reference's scene.Scene as rebuilt by the oracle from a SceneSpec."""
+
+    def __init__(self, spec: SceneSpec):
+        self._c = spec.to_c()
+        self._spec = spec
+        self._h = lib().oracle_scene_create(C.byref(self._c))
+        if not self._h:
+            raise ValueError("oracle_scene_create failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_scene_destroy(self._h)
+            self._h = None
+
+    def bvh(self):
+        n = lib().oracle_scene_num_nodes(self._h)
+        nodes = np.zeros(n, dtype=NODE_DTYPE)
+        perm = np.zeros(self._c.n_prims, dtype=np.int32)
+        lib().oracle_scene_bvh(self._h, nodes.ctypes.data, perm.ctypes.data)
+        return nodes, perm
+
+    def lights(self):
+        n = lib().oracle_scene_num_lights(self._h)
+        ids = np.zeros(n, dtype=np.int32)
+        lib().oracle_scene_lights(self._h, ids.ctypes.data)
+        return ids
+
+    def prim_bbox(self, i):
+        out = np.zeros(6)
+        lib().oracle_prim_bbox(self._h, i, out.ctypes.data)
+        return out
+
+    def triangle_fields(self, i):
+        out = np.zeros(22)
+        if lib().oracle_triangle_fields(self._h, i, out.ctypes.data) != 0:
+            raise TypeError("not a triangle")
+        return dict(edge1=out[0:3], edge2=out[3:6], normal=out[6:9], tangent=out[9:12], bitangent=out[12:15],
+                    area=out[15], bbmin=out[16:19], bbmax=out[19:22])
+
+    def hit(self, org, direction, tmin=0.0, tmax=np.finfo(np.float64).max, flavour=0):
+        o = np.ascontiguousarray(org, dtype=np.float64)
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        out = np.zeros(9)
+        pid = lib().oracle_hit(self._h, flavour, o.ctypes.data, d.ctypes.data, tmin, tmax, out.ctypes.data)
+        if pid < 0:
+            return None
+        return dict(prim=pid, t=out[0], u=out[1], v=out[2], p=out[3:6].copy(), normal=out[6:9].copy())
+
+    def trace(self, org, direction, tmin=0.001, tmax=np.finfo(np.float64).max, flavour=0, threads=None, stats=False):
+        o = np.ascontiguousarray(org, dtype=np.float64)
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        n = o.shape[0]
+        ids = np.empty(n, dtype=np.int32)
+        t = np.empty(n, dtype=np.float64)
+        st = Stats()
+        lib().oracle_trace(self._h, flavour, n, o.ctypes.data, d.ctypes.data, tmin, tmax, ids.ctypes.data,
+                           t.ctypes.data, C.byref(st) if stats else None, threads or os.cpu_count() or 1)
+        if stats:
+            return ids, t, {k: getattr(st, k) for k in ("nodes", "tris", "spheres", "others", "rays")}
+        return ids, t
+
+    def spectral_texture_value(self, tex, lam):
+        return lib().oracle_spectral_texture_value(self._h, tex, lam)
+
+    def render(self, width, height, spp, max_depth=50, sampler=0, rng_mode=0, flavour=0, threads=None, seed=1,
+               window=None, epilogue=True):
+        x0, y0, x1, y1 = window if window is not None else (0, 0, width - 1, height - 1)
+        p = RenderParams(width=width, height=height, spp=spp, max_depth=max_depth, sampler=sampler,
+                         rng_mode=rng_mode, flavour=flavour, threads=threads or os.cpu_count() or 1, seed=seed,
+                         x0=x0, y0=y0, x1=x1, y1=y1, epilogue=int(epilogue))
+        canvas = np.zeros((height, width, 4), dtype=np.float64)
+        rays = C.c_uint64()
+        lib().oracle_render(self._h, C.byref(p), canvas.ctypes.data, C.byref(rays))
+        return canvas, rays.value

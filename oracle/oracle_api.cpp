@@ -1,0 +1,338 @@
+// oracle_api.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+// Scene construction from izpi_scene_spec (the role of transport.ToScene, transport.go:53-92, and
+// of scenes.CornellBox, scenes.go:119-155), batched closest hit, and the tile render loop
+// (render/rgb.go:12-57, render/spectral.go:14-106, renderer.go:108-222).
+#include "oracle.h"
+#include "oracle_shade.hpp"
+
+#include <atomic>
+#include <cstring>
+#include <thread>
+
+using namespace orc;
+
+namespace orc {
+bool MaterialIsEmitter(const Material* m) { return m && m->IsEmitter(); }
+const Texture* MaterialNormalMap(const Material* m) { return (m && m->type == IZPI_MAT_PBR) ? m->normalMap : nullptr; }  // pbr.go:276, non_pbr.go:7
+Vec3 TextureValue(const Texture* t, double u, double v, const Vec3&) { return t->Value(u, v); }
+}  // namespace orc
+
+struct oracle_scene {
+  std::vector<std::unique_ptr<Hitable>> owned;
+  std::vector<Hitable*> hitables;  // reference's `hitables` slice, construction order
+  std::vector<Texture> textures;
+  std::vector<SpectralTexture> spectex;
+  std::vector<Material> materials;
+  std::unique_ptr<BVH4> bvh;
+  HitableSlice world, lights;
+  std::vector<int32_t> light_ids;
+  Camera camera;
+  izpi_camera_spec camspec;
+};
+
+static std::unique_ptr<Hitable> make_prim(const izpi_prim_spec& ps, int32_t id, const std::vector<Material>& mats) {
+  const Material* m = (ps.material >= 0 && ps.material < (int32_t)mats.size()) ? &mats[ps.material] : nullptr;
+  const double* p = ps.p;
+  std::unique_ptr<Hitable> h;
+  switch (ps.type) {
+    case IZPI_PRIM_TRIANGLE:
+      h = std::make_unique<Triangle>(V(p[0], p[1], p[2]), V(p[3], p[4], p[5]), V(p[6], p[7], p[8]), p[9], p[10], p[11],
+                                     p[12], p[13], p[14], m);
+      break;
+    case IZPI_PRIM_SPHERE: {
+      auto s = std::make_unique<Sphere>();
+      s->center0 = s->center1 = V(p[0], p[1], p[2]);
+      s->time0 = 0; s->time1 = 1;  // transport.go:679, scenes.go:133
+      s->radius = p[3]; s->material = m;
+      h = std::move(s);
+      break;
+    }
+    case IZPI_PRIM_XYRECT: case IZPI_PRIM_XZRECT: case IZPI_PRIM_YZRECT: {
+      auto r = std::make_unique<Rect>();
+      r->axis = ps.type == IZPI_PRIM_YZRECT ? 0 : (ps.type == IZPI_PRIM_XZRECT ? 1 : 2);
+      r->a0 = p[0]; r->a1 = p[1]; r->b0 = p[2]; r->b1 = p[3]; r->k = p[4]; r->material = m;
+      h = std::move(r);
+      break;
+    }
+    case IZPI_PRIM_BOX:
+      h = std::make_unique<Box>(V(p[0], p[1], p[2]), V(p[3], p[4], p[5]), m);
+      break;
+    default:
+      return nullptr;
+  }
+  h->prim_id = id;
+  if (ps.wrap & IZPI_WRAP_ROTATE_Y) {
+    auto r = std::make_unique<RotateY>();
+    r->h = std::move(h); r->init(ps.rotate_y_deg); r->prim_id = id;
+    h = std::move(r);
+  }
+  if (ps.wrap & IZPI_WRAP_TRANSLATE) {
+    auto t = std::make_unique<Translate>();
+    t->h = std::move(h); t->offset = V(ps.translate[0], ps.translate[1], ps.translate[2]); t->prim_id = id;
+    h = std::move(t);
+  }
+  if (ps.wrap & IZPI_WRAP_FLIP) {
+    auto f = std::make_unique<FlipNormals>();
+    f->h = std::move(h); f->prim_id = id;
+    h = std::move(f);
+  }
+  return h;
+}
+
+extern "C" {
+
+uint8_t oracle_ray_aabb4(int flavour, const float org[3], const float inv[3], const float b[24], float tmax) {
+  izpi_bvh4_node n;
+  std::memcpy(n.min_x, b, 96);
+  for (int i = 0; i < 4; i++) { n.child_index[i] = 0; n.primitive_count[i] = 0; }
+  return RayAABB4(flavour, org, inv, n, tmax);
+}
+float oracle_conservative_float32_min(double v) { return conservativeFloat32Min(v); }
+float oracle_conservative_float32_max(double v) { return conservativeFloat32Max(v); }
+double oracle_lcg_next(uint64_t* state) { Rng r; r.state = *state; double v = r.Float64(); *state = r.state; return v; }
+void oracle_sample_wavelength(double random, double* lambda, double* pdf) { SampleWavelength(random, *lambda, *pdf); }
+void oracle_cie_values(double lambda, double* xyz) { GetCIEValues(lambda, xyz[0], xyz[1], xyz[2]); }
+
+oracle_scene* oracle_scene_create(const izpi_scene_spec* spec) {
+  auto* s = new oracle_scene();
+  s->textures.resize(spec->n_textures);
+  for (int i = 0; i < spec->n_textures; i++) {
+    const izpi_texture_spec& t = spec->textures[i];
+    Texture& o = s->textures[i];
+    o.type = t.type; o.color = V(t.color[0], t.color[1], t.color[2]);
+    o.sizeX = t.width; o.sizeY = t.height; o.pixels = t.pixels;  // borrowed: caller keeps images alive
+  }
+  s->spectex.resize(spec->n_spectral_textures);
+  for (int i = 0; i < spec->n_spectral_textures; i++) {
+    const izpi_spectral_texture_spec& t = spec->spectral_textures[i];
+    SpectralTexture& o = s->spectex[i];
+    o.type = t.type; o.peak = t.peak; o.centre = t.centre; o.width = t.width;
+    if (t.type == IZPI_SPEC_TABULATED) {
+      o.spd.wavelengths.assign(t.wavelengths, t.wavelengths + t.n);
+      o.spd.values.assign(t.values, t.values + t.n);
+    }
+  }
+  auto tex = [&](int i) -> const Texture* { return (i >= 0 && i < (int)s->textures.size()) ? &s->textures[i] : nullptr; };
+  auto stex = [&](int i) -> const SpectralTexture* { return (i >= 0 && i < (int)s->spectex.size()) ? &s->spectex[i] : nullptr; };
+  s->materials.resize(spec->n_materials);
+  for (int i = 0; i < spec->n_materials; i++) {
+    const izpi_material_spec& m = spec->materials[i];
+    Material& o = s->materials[i];
+    o.type = m.type; o.tex = tex(m.tex); o.spectral = stex(m.spectral_tex);
+    o.spectralAbsorption = stex(m.spectral_absorption_tex);
+    o.normalMap = tex(m.normal_tex); o.roughness = tex(m.roughness_tex); o.metalness = tex(m.metalness_tex);
+    o.computeBeerLambert = m.compute_beer_lambert != 0;
+    o.v = V(m.v[0], m.v[1], m.v[2]); o.s = m.s;
+  }
+  for (int i = 0; i < spec->n_prims; i++) {
+    auto h = make_prim(spec->prims[i], i, s->materials);
+    if (!h) { delete s; return nullptr; }
+    s->hitables.push_back(h.get());
+    s->owned.push_back(std::move(h));
+  }
+  for (Hitable* h : s->hitables)  // transport.go:67-72, scenes.go:136-141
+    if (h->IsEmitter()) { s->lights.hitables.push_back(h); s->light_ids.push_back(h->prim_id); }
+  if (spec->world_kind == IZPI_WORLD_BVH4) {
+    Rng lcg; lcg.mode = 0; lcg.state = spec->bvh_seed;
+    s->bvh = newBVH4(s->hitables, &lcg, spec->bvh_rand_zero != 0);
+    if (s->bvh) s->world.hitables.push_back(s->bvh.get());
+    for (Material& m : s->materials)  // transport.go:83-89
+      if (m.type == IZPI_MAT_DIELECTRIC) m.world = &s->world;
+  } else {
+    s->world.hitables = s->hitables;
+  }
+  s->camspec = spec->camera;
+  s->camera.init(spec->camera);
+  return s;
+}
+void oracle_scene_destroy(oracle_scene* s) { delete s; }
+int32_t oracle_scene_num_nodes(const oracle_scene* s) { return s->bvh ? (int32_t)s->bvh->Nodes.size() : 0; }
+void oracle_scene_bvh(const oracle_scene* s, izpi_bvh4_node* nodes, int32_t* perm) {
+  if (!s->bvh) return;
+  std::memcpy(nodes, s->bvh->Nodes.data(), s->bvh->Nodes.size() * sizeof(izpi_bvh4_node));
+  std::memcpy(perm, s->bvh->PrimitiveIndices.data(), s->bvh->PrimitiveIndices.size() * sizeof(int32_t));
+}
+int32_t oracle_scene_num_lights(const oracle_scene* s) { return (int32_t)s->light_ids.size(); }
+void oracle_scene_lights(const oracle_scene* s, int32_t* ids) { std::memcpy(ids, s->light_ids.data(), s->light_ids.size() * 4); }
+void oracle_prim_bbox(const oracle_scene* s, int32_t prim, double* o) {
+  AABB b; s->hitables[prim]->BoundingBox(b);
+  o[0] = b.min.X; o[1] = b.min.Y; o[2] = b.min.Z; o[3] = b.max.X; o[4] = b.max.Y; o[5] = b.max.Z;
+}
+int oracle_triangle_fields(const oracle_scene* s, int32_t prim, double* o) {
+  auto* t = dynamic_cast<Triangle*>(s->hitables[prim]);
+  if (!t) return -1;
+  const Vec3* vs[5] = {&t->edge1, &t->edge2, &t->normal, &t->tangent, &t->bitangent};
+  for (int i = 0; i < 5; i++) { o[3 * i] = vs[i]->X; o[3 * i + 1] = vs[i]->Y; o[3 * i + 2] = vs[i]->Z; }
+  o[15] = t->area;
+  o[16] = t->bb.min.X; o[17] = t->bb.min.Y; o[18] = t->bb.min.Z; o[19] = t->bb.max.X; o[20] = t->bb.max.Y; o[21] = t->bb.max.Z;
+  return 0;
+}
+double oracle_spectral_texture_value(const oracle_scene* s, int32_t i, double lambda) { return s->spectex[i].Value(lambda); }
+
+int32_t oracle_hit(const oracle_scene* s, int flavour, const double org[3], const double dir[3], double tmin, double tmax,
+                   double* o) {
+  if (s->bvh) s->bvh->flavour = flavour;
+  Ray r = NewRay(V(org[0], org[1], org[2]), V(dir[0], dir[1], dir[2]), 0);
+  HitRecord rec; const Material* m;
+  if (!s->world.Hit(r, tmin, tmax, rec, m)) return -1;
+  o[0] = rec.t; o[1] = rec.u; o[2] = rec.v; o[3] = rec.p.X; o[4] = rec.p.Y; o[5] = rec.p.Z;
+  o[6] = rec.normal.X; o[7] = rec.normal.Y; o[8] = rec.normal.Z;
+  return rec.prim;
+}
+
+void oracle_trace(const oracle_scene* s, int flavour, int64_t n, const double* org, const double* dir, double tmin,
+                  double tmax, int32_t* prim_id, double* t, oracle_stats* stats, int threads) {
+  if (s->bvh) s->bvh->flavour = flavour;
+  if (threads < 1) threads = 1;
+  std::atomic<int64_t> next(0);
+  const int64_t chunk = 4096;  // rays handed out in chunks, like tiles from the work queue (renderer.go:172-188)
+  std::vector<Stats> st(threads);
+  auto work = [&](int tid) {
+    g_stats = stats ? &st[tid] : nullptr;
+    for (;;) {
+      int64_t b = next.fetch_add(chunk);
+      if (b >= n) break;
+      int64_t e = b + chunk < n ? b + chunk : n;
+      for (int64_t i = b; i < e; i++) {
+        Ray r = NewRay(V(org[3 * i], org[3 * i + 1], org[3 * i + 2]), V(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), 0);
+        HitRecord rec; const Material* m;
+        if (s->world.Hit(r, tmin, tmax, rec, m)) { prim_id[i] = rec.prim; t[i] = rec.t; }
+        else { prim_id[i] = -1; t[i] = 0.0; }
+      }
+    }
+    g_stats = nullptr;
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < threads; i++) th.emplace_back(work, i);
+  work(0);
+  for (auto& x : th) x.join();
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    for (auto& x : st) { stats->nodes += x.nodes; stats->tris += x.tris; stats->spheres += x.spheres; stats->others += x.others; }
+    stats->rays = (uint64_t)n;
+  }
+}
+
+void oracle_tiles(int32_t sx, int32_t sy, int32_t* stepx, int32_t* stepy) {  // common/tiles.go:3-24
+  static const int sizes[10] = {32, 25, 24, 20, 16, 12, 10, 8, 5, 4};
+  *stepx = 0; *stepy = 0;
+  for (int s : sizes) if (sx % s == 0) { *stepx = s; break; }
+  for (int s : sizes) if (sy % s == 0) { *stepy = s; break; }
+}
+
+void oracle_render(const oracle_scene* s, const oracle_render_params* p, double* canvas, uint64_t* num_rays) {
+  if (s->bvh) s->bvh->flavour = p->flavour;
+  const int nx = p->width, ny = p->height;
+  int threads = p->threads < 1 ? 1 : p->threads;
+  std::atomic<int> nextRow(p->y0);
+  std::atomic<uint64_t> rays(0);
+  // camera.New with the aspect override W/H (leader.go:45, transport.go:534-539)
+  Camera cam = s->camera;
+  auto work = [&]() {
+    Sampler smp;
+    smp.maxDepth = p->max_depth;
+    smp.background = Vec3();  // colours.Black
+    smp.spectralBackground.wavelengths = {380, 750};  // colours.SpectralBlack (colours.go:19): all-zero SPD
+    smp.spectralBackground.values = {0, 0};
+    for (;;) {
+      int y = nextRow.fetch_add(1);
+      if (y > p->y1) break;
+      Rng rng, camRng;  // mode 0: one private LCG per work unit + the camera's own LCG (camera.go:14,46)
+      rng.mode = 0; rng.state = Rng::mix64(p->seed + 0x1000003ull * (uint64_t)y) & 0xffffffffull;
+      camRng.mode = 0; camRng.state = Rng::mix64(p->seed ^ (0xC0FFEEull + (uint64_t)y)) & 0xffffffffull;
+      for (int x = p->x0; x <= p->x1; x++) {
+        double a0 = 0, a1 = 0, a2 = 0;
+        for (int smpl = 0; smpl < p->spp; smpl++) {
+          Rng* r = &rng; Rng* cr = &camRng;
+          Rng ctr;
+          if (p->rng_mode == 1) {
+            ctr.mode = 1; ctr.key = Rng::stream_key(p->seed, (uint64_t)y * (uint64_t)nx + (uint64_t)x, (uint64_t)smpl); ctr.ctr = 0;
+            r = &ctr; cr = &ctr;
+          }
+          if (p->sampler == 0) {  // rgb.go:30-37
+            double u = ((double)x + r->Float64()) / (double)nx;
+            double v = ((double)y + r->Float64()) / (double)ny;
+            Ray ray = cam.GetRay(u, v, 0, *cr);
+            Vec3 c = DeNAN(smp.Sample(ray, &s->world, &s->lights, 0, *r));
+            a0 = a0 + c.X; a1 = a1 + c.Y; a2 = a2 + c.Z;
+          } else {  // render/spectral.go:75-96
+            double lambda, pdf;
+            SampleWavelength(r->Float64(), lambda, pdf);
+            if (pdf == 0) continue;
+            double u = ((double)x + r->Float64()) / (double)nx;
+            double v = ((double)y + r->Float64()) / (double)ny;
+            Ray ray = cam.GetRay(u, v, lambda, *cr);
+            double radiance = smp.SampleSpectral(ray, &s->world, &s->lights, 0, *r);
+            double cx, cy, cz;
+            GetCIEValues(lambda, cx, cy, cz);
+            a0 += (radiance * cx) / pdf; a1 += (radiance * cy) / pdf; a2 += (radiance * cz) / pdf;
+          }
+        }
+        if (p->sampler == 0) { a0 = a0 / (double)p->spp; a1 = a1 / (double)p->spp; a2 = a2 / (double)p->spp; }  // rgb.go:39
+        else { double inv = 1.0 / (double)p->spp; a0 = a0 * inv; a1 = a1 * inv; a2 = a2 * inv; }             // spectral.go:99-103
+        int row = ny - y;  // rgb.go:41: canvas.Set(x, ny-y, ...); row ny is out of bounds -> dropped
+        if (row >= 0 && row < ny) {
+          double* px = canvas + ((size_t)row * nx + x) * 4;
+          px[0] = a0; px[1] = a1; px[2] = a2; px[3] = 1.0;
+        }
+      }
+    }
+    rays.fetch_add(smp.numRays);
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < threads; i++) th.emplace_back(work);
+  work();
+  for (auto& x : th) x.join();
+  if (num_rays) *num_rays = rays.load();
+  if (p->sampler == 1 && p->epilogue) {  // renderer.go:216-219
+    oracle_firefly_rejection(canvas, nx, ny);
+    std::vector<double> tmp(canvas, canvas + (size_t)4 * nx * ny);
+    oracle_xyz_to_rgb(tmp.data(), canvas, nx, ny, cam.exposure);
+  }
+}
+
+void oracle_firefly_rejection(double* pix, int32_t width, int32_t height) {  // firefly_rejection.go:12-113
+  if (width == 0 || height == 0) return;
+  const int kernelRadius = 1; const double kThreshold = 2.5; const int minNeighbors = 3;
+  std::vector<double> yValues((size_t)width * height);
+  for (int y = 0; y < height; y++) for (int x = 0; x < width; x++) yValues[(size_t)y * width + x] = pix[((size_t)y * width + x) * 4 + 1];
+  for (int y = 0; y < height; y++) for (int x = 0; x < width; x++) {
+    size_t pixelIdx = ((size_t)y * width + x) * 4;
+    double currentY = yValues[(size_t)y * width + x];
+    if (currentY <= 0) continue;
+    double nb[8]; int n = 0;
+    for (int dy = -kernelRadius; dy <= kernelRadius; dy++) for (int dx = -kernelRadius; dx <= kernelRadius; dx++) {
+      if (dx == 0 && dy == 0) continue;
+      int nx = x + dx, ny = y + dy;
+      if (nx >= 0 && nx < width && ny >= 0 && ny < height) {
+        double v = yValues[(size_t)ny * width + nx];
+        if (v > 0) nb[n++] = v;
+      }
+    }
+    if (n < minNeighbors) continue;
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) sum += nb[i];
+    double mean = sum / (double)n;
+    double varianceSum = 0.0;
+    for (int i = 0; i < n; i++) { double d = nb[i] - mean; varianceSum += d * d; }
+    double stddev = std::sqrt(varianceSum / (double)n);
+    double threshold = mean + kThreshold * stddev;
+    if (currentY > threshold && threshold > 0) {
+      double ratio = threshold / currentY;
+      pix[pixelIdx] *= ratio; pix[pixelIdx + 1] *= ratio; pix[pixelIdx + 2] *= ratio;
+    }
+  }
+}
+
+void oracle_xyz_to_rgb(const double* in, double* out, int32_t width, int32_t height, double exposure) {  // rgb_image.go:13-67
+  static const double M[3][3] = {{1.6410234, -0.3248033, -0.2364247}, {-0.6636629, 1.6153316, 0.0167563}, {0.0117219, -0.0082845, 0.9883949}};
+  for (size_t i = 0; i < (size_t)width * height; i++) {
+    double x = in[4 * i] * exposure, y = in[4 * i + 1] * exposure, z = in[4 * i + 2] * exposure;
+    out[4 * i] = M[0][0] * x + M[0][1] * y + M[0][2] * z;
+    out[4 * i + 1] = M[1][0] * x + M[1][1] * y + M[1][2] * z;
+    out[4 * i + 2] = M[2][0] * x + M[2][1] * y + M[2][2] * z;
+    out[4 * i + 3] = in[4 * i + 3];
+  }
+}
+
+}  // extern "C"
