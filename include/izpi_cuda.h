@@ -1,0 +1,175 @@
+/*
+ * izpi_cuda.h -- C ABI of libizpi_cuda.so, the B200 (sm_100a) backend for Izpi's hot path.
+ *
+ * This is what a cgo package `internal/cuda` binds (INTEGRATION.md shows the stub).  The
+ * reference has no FFI seam; each entry point replaces one of its Go seams:
+ *
+ *   izpi_scene_upload    <- the scene.Scene object graph produced by transport.ToScene()
+ *                           (internal/transport/transport.go:53-92): BVH4.Nodes / BVH4.Primitives
+ *                           (internal/hitable/bvh4.go:42-47) flattened by package hitable,
+ *                           material/texture tables flattened by packages material/texture.
+ *   izpi_trace_closest   <- hitable.Hitable.Hit(r, tMin, tMax) (internal/hitable/api.go:15) as
+ *                           implemented by *BVH4 (bvh4.go:49-164) under HitableSlice.Hit
+ *                           (hitable_slice.go:30-45), batched (a cgo call per ray costs ~35 ns,
+ *                           bvh4_simd_arm64.go:14, so the boundary is per batch).
+ *   izpi_render_setup    <- render.New(...) (internal/render/renderer.go:73-106) and
+ *                           RenderSetup (internal/proto/control/control.proto:56-68).
+ *   izpi_render_tiles    <- renderRectRGB / renderRectSpectral (render/rgb.go:12,
+ *                           render/spectral.go:14) and worker.RenderTile
+ *                           (internal/worker/render.go:17-75), for a batch of tiles.
+ *   izpi_render_finish   <- the tail of RendererImpl.Render (renderer.go:213-221):
+ *                           FireflyRejection + XYZToRGB for the spectral sampler, ray total.
+ *
+ * Conventions: every function returns 0 on success and a negative IZPI_E* code on failure;
+ * izpi_last_error() returns a thread-local message (the Go side wraps it into `error`).  All
+ * pointers are borrowed for the duration of the call (cgo rule); uploads copy; outputs are
+ * caller-allocated host memory unless the name says `_device`.  Calls on different contexts are
+ * thread-safe; calls on one context must be serialised by the caller (one goroutine per GPU,
+ * runtime.LockOSThread).  There is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef IZPI_CUDA_H
+#define IZPI_CUDA_H
+
+#include <stdint.h>
+#include "izpi_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IZPI_OK 0
+#define IZPI_EINVAL (-1)  /* bad argument                         */
+#define IZPI_ECUDA (-2)   /* CUDA runtime error / no device       */
+#define IZPI_ESTATE (-3)  /* call out of order (no scene, no setup) */
+
+typedef struct izpi_ctx izpi_ctx;
+
+const char* izpi_last_error(void);
+int izpi_version(void);
+
+/* One context per GPU.  n_devices must be 1 in this release: the process-per-GPU model
+ * (one rank per device, NCCL through the host runtime) is the multi-GPU path. */
+int izpi_ctx_create(int n_devices, const int* device_ids, izpi_ctx** out);
+void izpi_ctx_destroy(izpi_ctx* ctx);
+
+/* ---- flattened scene ------------------------------------------------------------------
+ * Device primitive record, 80 bytes, 16-byte aligned, stored in WORLD ORDER: the BVH4's
+ * reordered Primitives order (bvh4.go:585-590) when the world is a BVH4, else the
+ * HitableSlice order.  A 4-primitive leaf is 320 contiguous bytes. */
+typedef struct izpi_prim_rec {
+  /* TRIANGLE: vertex0.xyz edge1.xyz edge2.xyz      (triangle.go:22-34)
+   * SPHERE:   center.xyz radius                    (sphere.go:21-27)
+   * X?RECT:   a0 a1 b0 b1 k                        (xyrect.go:18-25 ...)
+   * BOX:      pMin.xyz pMax.xyz                    (box.go:16-21) */
+  double a[9];
+  int32_t orig_id; /* index in the construction-order hitables list (what Hit callers see) */
+  uint32_t tag;    /* bits 0-2 IZPI_PRIM_*, bit 3 FlipNormals, bits 4-17 material, bits 18-31 xform index + 1 (0 = none) */
+} izpi_prim_rec;
+
+#define IZPI_TAG(type, flip, material, xform1) \
+  ((uint32_t)(type) | ((uint32_t)((flip) ? 1 : 0) << 3) | ((uint32_t)(material) << 4) | ((uint32_t)(xform1) << 18))
+
+/* Shading attributes of a triangle, same index as its record (triangle.go:35-50). 128 bytes. */
+typedef struct izpi_tri_attr {
+  double normal[3], tangent[3], bitangent[3];
+  double uv[6]; /* u0 v0 u1 v1 u2 v2 */
+  double area;
+} izpi_tri_attr;
+
+/* Translate(RotateY(.)) wrapper chain (translate.go:16-19, rotate_y.go:19-25). */
+typedef struct izpi_xform {
+  double sin_theta, cos_theta; /* RotateY; identity = 0, 1 */
+  double offset[3];            /* Translate; identity = 0   */
+  int32_t has_rotate, has_translate;
+} izpi_xform;
+
+/* Thin-lens camera, fields of camera.Camera after camera.New (camera/camera.go:13-58). */
+typedef struct izpi_camera {
+  double lens_radius, time0, time1, exposure;
+  double u[3], v[3], origin[3], lower_left_corner[3], horizontal[3], vertical[3];
+} izpi_camera;
+
+typedef struct izpi_scene_desc {
+  int32_t world_kind; /* IZPI_WORLD_SLICE | IZPI_WORLD_BVH4 */
+  int32_t n_nodes;
+  const izpi_bvh4_node* nodes; /* BVH4.Nodes verbatim (128 B each) */
+  int32_t n_prims;
+  int32_t n_xforms;
+  const izpi_prim_rec* prims;
+  const izpi_tri_attr* tri_attrs; /* [n_prims]; entries of non-triangles are ignored; may be NULL for trace-only use */
+  const izpi_xform* xforms;
+  int32_t n_lights;
+  int32_t n_materials;
+  const int32_t* lights; /* record indices of the scene.Lights members, in Lights order */
+  const izpi_material_spec* materials;
+  int32_t n_textures, n_spectral_textures;
+  const izpi_texture_spec* textures;
+  const izpi_spectral_texture_spec* spectral_textures;
+  izpi_camera camera;
+  int32_t dielectric_has_world; /* Dielectric.SetWorld was called (transport.go:83-89) */
+  int32_t reserved;
+} izpi_scene_desc;
+
+int izpi_scene_upload(izpi_ctx* ctx, const izpi_scene_desc* desc);
+
+/* ---- closest hit ------------------------------------------------------------------------ */
+#define IZPI_TRACE_EXACT 0 /* reference traversal order, fp32 SSE-flavour box test, fp64 primitives: bit-exact */
+#define IZPI_TRACE_FP32 1  /* optional: fp32 primitive tests, reported separately (not parity-checked bitwise) */
+
+typedef struct izpi_trace_stats {
+  uint64_t rays, nodes_visited, prim_tests; /* filled when requested (slower counting kernel) */
+  double kernel_ms;                         /* device time of the traversal kernel alone */
+} izpi_trace_stats;
+
+/* org/dir: n*3 doubles (xyz interleaved).  prim_id[i] = orig_id of the closest primitive or -1;
+ * t[i] = hit parameter (0 on miss).  Host buffers; copies are part of the call. */
+int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org_xyz, const double* dir_xyz, double tmin,
+                       double tmax, int mode, int32_t* prim_id, double* t, izpi_trace_stats* stats_opt);
+/* Same, all four buffers already resident in this context's device memory; launched on `stream`
+ * (a cudaStream_t, NULL = the context's stream) and NOT synchronised. */
+int izpi_trace_closest_device(izpi_ctx* ctx, int64_t n, const double* d_org_xyz, const double* d_dir_xyz,
+                              double tmin, double tmax, int mode, int32_t* d_prim_id, double* d_t, void* stream);
+/* Counts the kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t izpi_launch_count(const izpi_ctx* ctx);
+
+/* Diagnostic (not part of the drop-in surface): the 4-wide fp32 slab test alone, n independent
+ * cases -- RayAABB4_SIMD (bvh4_simd_amd64.go:27) -- so the reference's golden masks
+ * (bvh4_simd_test.go:54-268) can be replayed on the device.  org/inv: n*3 floats; bounds: n*24 floats
+ * (minX[4] minY[4] minZ[4] maxX[4] maxY[4] maxZ[4]); tmax: n floats; masks: n bytes. */
+int izpi_debug_ray_aabb4(izpi_ctx* ctx, int32_t n, const float* org, const float* inv, const float* bounds,
+                         const float* tmax, uint8_t* masks);
+
+/* ---- tile rendering --------------------------------------------------------------------- */
+#define IZPI_SAMPLER_COLOUR 0   /* sampler/colour.go   */
+#define IZPI_SAMPLER_SPECTRAL 1 /* sampler/spectral.go */
+
+typedef struct izpi_render_config {
+  int32_t width, height, spp, max_depth;
+  int32_t sampler;
+  int32_t sample_offset; /* first global sample index rendered by this context (sample-range sharding) */
+  int32_t sample_count;  /* samples of every pixel rendered by this context; the mean still divides by spp */
+  int32_t reserved;
+  double background[3];        /* colours.Black by default */
+  const double* bg_wavelengths; /* spectral background SPD (control.proto:64-67); NULL = SpectralBlack */
+  const double* bg_values;
+  int32_t n_bg;
+  int32_t reserved2;
+  uint64_t seed;
+} izpi_render_config;
+
+int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg);
+/* tiles: n_tiles * 4 uint32 {x0, y0, x1, y1}, inclusive pixel bounds in the reference's workUnit
+ * convention (renderer.go:183-186).  Accumulates into the device canvas; if canvas_rgba is not
+ * NULL the rendered tiles' pixels are also written there (4*W*H doubles, Float64NRGBA layout,
+ * reference row flip rgb.go:41). */
+int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* x0y0x1y1, double* canvas_rgba);
+/* Device pointer of the context's canvas accumulator (4*W*H doubles: per-pixel SUMS over the
+ * samples rendered so far, alpha = 1 where written) so that the host runtime can ncclReduce it. */
+int izpi_render_canvas_device(izpi_ctx* ctx, double** d_canvas);
+/* Divide by spp, apply the epilogue (spectral: FireflyRejection + XYZ->ACEScg), copy to host. */
+int izpi_render_finish(izpi_ctx* ctx, double* canvas_rgba, uint64_t* total_rays);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IZPI_CUDA_H */

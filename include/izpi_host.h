@@ -1,0 +1,51 @@
+/*
+ * izpi_host.h -- C++ host runtime above the device C ABI, exported with C linkage for harnesses.
+ *
+ * Stand-in for the Go packages that change in a real deployment (BASELINE.json north_star (1),(5)):
+ * it does what the modified internal/hitable, internal/material, internal/texture, internal/camera
+ * and internal/render would do on the host -- run the object constructors, build the BVH4
+ * (hitable.NewBVH4, bvh4.go:517), flatten everything into izpi_scene_desc, schedule tiles -- and
+ * then calls the izpi_cuda.h entry points.  The Go toolchain is absent from this image, so the
+ * host side is C++ (the reference is compiled code); INTEGRATION.md maps each function to the Go
+ * code that would replace it.
+ */
+#ifndef IZPI_HOST_H
+#define IZPI_HOST_H
+
+#include "izpi_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct izpi_host_scene izpi_host_scene;
+
+/* transport.ToScene() (transport.go:53-92) / scenes.CornellBox (scenes.go:119-155): constructors,
+ * lights = emitters, world = BVH4 or slice, camera.New.  `threads` parallelises the BVH build
+ * (result is independent of it). */
+int izpi_host_scene_create(const izpi_scene_spec* spec, int threads, izpi_host_scene** out);
+void izpi_host_scene_destroy(izpi_host_scene* s);
+
+/* BVH4.Nodes and the Primitives permutation (bvh4.go:42-47): Primitives[i] = hitables[perm[i]]. */
+int32_t izpi_host_scene_num_nodes(const izpi_host_scene* s);
+int izpi_host_scene_bvh(const izpi_host_scene* s, izpi_bvh4_node* nodes, int32_t* perm);
+int32_t izpi_host_scene_num_lights(const izpi_host_scene* s);
+int izpi_host_scene_lights(const izpi_host_scene* s, int32_t* orig_ids);
+
+/* The flattened description (pointers stay valid until the host scene is destroyed). */
+int izpi_host_scene_desc(const izpi_host_scene* s, izpi_scene_desc* out);
+int izpi_host_scene_upload(const izpi_host_scene* s, izpi_ctx* ctx);
+
+/* common.Tiles (common/tiles.go:6-24); 0 when no listed size divides the dimension. */
+void izpi_host_tiles(int32_t size_x, int32_t size_y, int32_t* step_x, int32_t* step_y);
+
+/* RendererImpl.Render (renderer.go:108-222) for the local path on one context: tile grid from
+ * common.Tiles, tiles [tile_begin, tile_end) of the row-major grid submitted in batches, then
+ * izpi_render_finish when `finish` is set.  tile_end = -1 means all tiles. */
+int izpi_host_render(izpi_ctx* ctx, const izpi_render_config* cfg, int32_t tile_begin, int32_t tile_end,
+                     int32_t finish, double* canvas_rgba, uint64_t* total_rays);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IZPI_HOST_H */

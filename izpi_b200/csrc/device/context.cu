@@ -1,0 +1,133 @@
+// context.cu -- izpi_ctx lifetime and the one-time scene upload (include/izpi_cuda.h).
+#include <cstring>
+
+#include "dscene.cuh"
+
+using namespace izpi;
+
+void render_state_free(izpi_ctx* ctx);  // render.cu
+
+namespace {
+
+template <typename T>
+int upload(izpi_ctx* ctx, const T* host, size_t count, const T** dev, size_t align_bytes = 256) {
+  *dev = nullptr;
+  if (count == 0) return IZPI_OK;
+  void* p = nullptr;
+  IZ_CUDA(cudaMalloc(&p, count * sizeof(T)));  // cudaMalloc is 256-byte aligned
+  (void)align_bytes;
+  ctx->scene_allocs.push_back(p);
+  IZ_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *dev = static_cast<const T*>(p);
+  return IZPI_OK;
+}
+
+void free_scene(izpi_ctx* ctx) {
+  for (void* p : ctx->scene_allocs) cudaFree(p);
+  ctx->scene_allocs.clear();
+  ctx->has_scene = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int izpi_ctx_create(int n_devices, const int* device_ids, izpi_ctx** out) {
+  if (!out) { set_error("izpi_ctx_create: out is NULL"); return IZPI_EINVAL; }
+  *out = nullptr;
+  if (n_devices != 1) { set_error("izpi_ctx_create: one device per context (process-per-GPU model)"); return IZPI_EINVAL; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error(std::string("izpi_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    return IZPI_ECUDA;
+  }
+  int dev = device_ids ? device_ids[0] : 0;
+  if (dev < 0 || dev >= count) { set_error("izpi_ctx_create: device id out of range"); return IZPI_EINVAL; }
+  IZ_CUDA(cudaSetDevice(dev));
+  auto* ctx = new izpi_ctx();
+  ctx->device = dev;
+  cudaDeviceProp prop;
+  IZ_CUDA(cudaGetDeviceProperties(&prop, dev));
+  ctx->sm_count = prop.multiProcessorCount;
+  IZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  IZ_CUDA(cudaEventCreate(&ctx->ev0));
+  IZ_CUDA(cudaEventCreate(&ctx->ev1));
+  IZ_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+  IZ_CUDA(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
+  *out = ctx;
+  return IZPI_OK;
+}
+
+void izpi_ctx_destroy(izpi_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  render_state_free(ctx);
+  free_scene(ctx);
+  cudaFree(ctx->d_org); cudaFree(ctx->d_dir); cudaFree(ctx->d_ids); cudaFree(ctx->d_t); cudaFree(ctx->d_counters);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int izpi_scene_upload(izpi_ctx* ctx, const izpi_scene_desc* d) {
+  if (!ctx || !d) { set_error("izpi_scene_upload: bad argument"); return IZPI_EINVAL; }
+  if (d->n_prims < 0 || d->n_nodes < 0 || (d->n_prims > 0 && !d->prims) || (d->n_nodes > 0 && !d->nodes)) {
+    set_error("izpi_scene_upload: inconsistent primitive / node arrays");
+    return IZPI_EINVAL;
+  }
+  if (d->world_kind == IZPI_WORLD_BVH4 && d->n_prims > 0 && d->n_nodes == 0) {
+    set_error("izpi_scene_upload: BVH4 world without nodes");
+    return IZPI_EINVAL;
+  }
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  IZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  free_scene(ctx);
+  DScene& s = ctx->scene;
+  std::memset(&s, 0, sizeof(s));
+  s.world_kind = d->world_kind; s.n_nodes = d->n_nodes; s.n_prims = d->n_prims; s.n_xforms = d->n_xforms;
+  s.n_lights = d->n_lights; s.n_materials = d->n_materials; s.dielectric_has_world = d->dielectric_has_world;
+  s.camera = d->camera;
+  int rc;
+  const izpi_bvh4_node* dn = nullptr;
+  if ((rc = upload(ctx, d->nodes, (size_t)d->n_nodes, &dn)) != IZPI_OK) return rc;
+  s.nodes = reinterpret_cast<const float4*>(dn);
+  if ((rc = upload(ctx, d->prims, (size_t)d->n_prims, &s.prims)) != IZPI_OK) return rc;
+  if (d->tri_attrs && (rc = upload(ctx, d->tri_attrs, (size_t)d->n_prims, &s.attrs)) != IZPI_OK) return rc;
+  if ((rc = upload(ctx, d->xforms, (size_t)d->n_xforms, &s.xforms)) != IZPI_OK) return rc;
+  if ((rc = upload(ctx, d->lights, (size_t)d->n_lights, &s.lights)) != IZPI_OK) return rc;
+  if ((rc = upload(ctx, d->materials, (size_t)d->n_materials, &s.materials)) != IZPI_OK) return rc;
+  // textures: pixel arrays first, then the table that points at them
+  std::vector<DTexture> tex((size_t)d->n_textures);
+  for (int i = 0; i < d->n_textures; i++) {
+    const izpi_texture_spec& t = d->textures[i];
+    DTexture& o = tex[i];
+    std::memset(&o, 0, sizeof(o));
+    o.type = t.type; o.width = t.width; o.height = t.height;
+    for (int k = 0; k < 3; k++) o.color[k] = t.color[k];
+    if (t.type == IZPI_TEX_IMAGE) {
+      if (!t.pixels || t.width <= 0 || t.height <= 0) { set_error("izpi_scene_upload: image texture without pixels"); return IZPI_EINVAL; }
+      if ((rc = upload(ctx, t.pixels, (size_t)t.width * t.height * 4, &o.pixels)) != IZPI_OK) return rc;
+    }
+  }
+  if ((rc = upload(ctx, tex.data(), tex.size(), &s.textures)) != IZPI_OK) return rc;
+  std::vector<DSpectralTexture> st((size_t)d->n_spectral_textures);
+  for (int i = 0; i < d->n_spectral_textures; i++) {
+    const izpi_spectral_texture_spec& t = d->spectral_textures[i];
+    DSpectralTexture& o = st[i];
+    std::memset(&o, 0, sizeof(o));
+    o.type = t.type; o.n = t.n; o.peak = t.peak; o.centre = t.centre; o.width = t.width;
+    if (t.type == IZPI_SPEC_TABULATED) {
+      if ((rc = upload(ctx, t.wavelengths, (size_t)t.n, &o.wavelengths)) != IZPI_OK) return rc;
+      if ((rc = upload(ctx, t.values, (size_t)t.n, &o.values)) != IZPI_OK) return rc;
+    }
+  }
+  if ((rc = upload(ctx, st.data(), st.size(), &s.spectex)) != IZPI_OK) return rc;
+  IZ_CUDA(cudaStreamSynchronize(ctx->stream));  // borrowed host memory is free to go after this call
+  ctx->has_scene = true;
+  return IZPI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// dscene.cuh -- the scene as it lives in HBM (uploaded once by izpi_scene_upload) and the
+// per-context state.  Layout rationale in DESIGN.md §3.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../../include/izpi_cuda.h"
+#include "../common/vecmath.h"
+
+namespace izpi {
+
+void set_error(const std::string& msg);
+
+struct DTexture {  // texture.Constant / texture.ImageTxt
+  int32_t type, width, height, pad;
+  double color[3];
+  const double* pixels;  // device, RGBA fp64 (32 B per texel, 16-B aligned)
+};
+struct DSpectralTexture {  // texture.SpectralConstant
+  int32_t type, n;
+  double peak, centre, width;
+  const double* wavelengths;  // device
+  const double* values;       // device
+};
+
+struct DScene {
+  int32_t world_kind, n_nodes, n_prims, n_xforms, n_lights, n_materials, dielectric_has_world, pad;
+  const float4* nodes;          // 8 x float4 per BVH4Node, 128-B aligned
+  const izpi_prim_rec* prims;   // 80-B records in world order, 16-B aligned
+  const izpi_tri_attr* attrs;   // 128-B records, same index
+  const izpi_xform* xforms;
+  const int32_t* lights;        // record indices
+  const izpi_material_spec* materials;
+  const DTexture* textures;
+  const DSpectralTexture* spectex;
+  izpi_camera camera;
+};
+
+#define IZ_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      izpi::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+      return IZPI_ECUDA;                                                                      \
+    }                                                                                         \
+  } while (0)
+
+}  // namespace izpi
+
+struct RenderState;  // render.cu
+
+struct izpi_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool has_scene = false;
+  izpi::DScene scene{};
+  std::vector<void*> scene_allocs;  // freed on re-upload / destroy
+  // trace scratch (grown on demand)
+  double* d_org = nullptr; double* d_dir = nullptr; int32_t* d_ids = nullptr; double* d_t = nullptr;
+  int64_t ray_capacity = 0;
+  unsigned long long* d_counters = nullptr;  // [0] work-queue head, [1] nodes visited, [2] primitive tests
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint64_t launches = 0;
+  RenderState* render = nullptr;
+};

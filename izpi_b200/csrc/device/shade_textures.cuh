@@ -1,0 +1,53 @@
+// shade_textures.cuh -- texture lookups on the device.
+//   texture_value()   <- Constant.Value (texture/constant.go:21), ImageTxt.Value (texture/image.go:73-101)
+//   spectral_value()  <- SpectralConstant.Value (texture/spectral_constant.go:65-106)
+#pragma once
+#include "dscene.cuh"
+
+namespace izpi {
+
+// Go's int(float64): truncation toward zero; NaN / out-of-range convert to MinInt64 on amd64
+// (CVTTSD2SQ), which the clamps below turn into 0.
+__device__ __forceinline__ long long go_int(double x) {
+  if (!(x > -9.2e18 && x < 9.2e18)) return (long long)0x8000000000000000ull;
+  return (long long)x;
+}
+
+__device__ __forceinline__ d3 texture_value(const DScene& sc, int tex, double u, double v) {
+  const DTexture& t = sc.textures[tex];
+  if (t.type == IZPI_TEX_CONSTANT) return mk(t.color[0], t.color[1], t.color[2]);
+  long long i = go_int(u * (double)t.width);
+  long long j = go_int((1 - v) * ((double)t.height - 0.001));
+  if (i < 0) i = 0;
+  if (j < 0) j = 0;
+  if (i > t.width - 1) i = t.width - 1;
+  if (j > t.height - 1) j = t.height - 1;
+  const double2* px = reinterpret_cast<const double2*>(t.pixels + ((size_t)j * t.width + (size_t)i) * 4);
+  double2 rg = __ldg(px);
+  double b = __ldg(reinterpret_cast<const double*>(px + 1));
+  return mk(rg.x, rg.y, b);
+}
+
+__device__ __forceinline__ double spd_interp(const double* w, const double* val, int n, double lambda) {
+  // interpolateSPD (spectral_constant.go:78-106): clamp outside, first bracketing pair inside
+  if (n == 0) return 0.0;
+  if (lambda < w[0]) return val[0];
+  if (lambda > w[n - 1]) return val[n - 1];
+  for (int i = 0; i < n - 1; i++) {
+    double w1 = w[i], w2 = w[i + 1];
+    if (lambda >= w1 && lambda <= w2) {
+      double t = (lambda - w1) / (w2 - w1);
+      return val[i] + t * (val[i + 1] - val[i]);
+    }
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ double spectral_value(const DScene& sc, int tex, double lambda) {
+  const DSpectralTexture& t = sc.spectex[tex];
+  if (t.type == IZPI_SPEC_TABULATED) return spd_interp(t.wavelengths, t.values, t.n, lambda);
+  double e = (lambda - t.centre) / t.width;
+  return t.peak * exp(-(e * e));  // math.Pow(x, 2) is exactly x*x
+}
+
+}  // namespace izpi

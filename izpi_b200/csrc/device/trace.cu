@@ -1,0 +1,162 @@
+// trace.cu -- batched closest hit: the hitable.Hitable.Hit seam (internal/hitable/api.go:15) for a
+// whole ray batch.  Persistent warps pull 32-ray packets from a global work queue; each lane walks
+// the BVH4 in the reference's order with its own short stack in shared memory.
+#include <cstring>
+
+#include "intersect.cuh"
+
+using namespace izpi;
+
+namespace {
+
+constexpr int kTraceThreads = 128;
+constexpr int kStackDepth = 64;  // bvh4.go:71
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads)
+trace_kernel(const __grid_constant__ DScene sc, long long n, const double* __restrict__ org,
+             const double* __restrict__ dir, double tmin, double tmax, int32_t* __restrict__ ids,
+             double* __restrict__ ts, unsigned long long* counters) {
+  extern __shared__ int32_t stack_smem[];  // [kStackDepth][blockDim.x]: lane-interleaved, conflict-free
+  int32_t* stack = stack_smem + threadIdx.x;
+  const int stride = blockDim.x;
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t n_nodes = 0, n_prims = 0;
+  for (;;) {
+    long long base = 0;
+    if (lane == 0) base = (long long)atomicAdd(&counters[0], 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    long long i = base + lane;
+    if (i < n) {
+      DRay r;
+      r.o = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
+      r.d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+      r.time = 0; r.lambda = 0;
+      double t = 0;
+      int rec = world_closest<COUNT>(sc, r, tmin, tmax, t, stack, stride, n_nodes, n_prims);
+      ids[i] = rec >= 0 ? sc.prims[rec].orig_id : -1;
+      ts[i] = rec >= 0 ? t : 0.0;
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&counters[1], (unsigned long long)n_nodes);
+    atomicAdd(&counters[2], (unsigned long long)n_prims);
+  }
+}
+
+// Diagnostic: the 4-wide slab test alone, so the reference's golden masks can be replayed on the device.
+__global__ void box4_kernel(int n, const float* __restrict__ org, const float* __restrict__ inv,
+                            const float* __restrict__ bounds, const float* __restrict__ tmax, uint8_t* __restrict__ masks) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* o = org + 3 * i; const float* v = inv + 3 * i; const float* b = bounds + 24 * i;
+  uint8_t m = 0;
+  for (int k = 0; k < 4; k++)
+    if (box1(o[0], o[1], o[2], v[0], v[1], v[2], b[k], b[4 + k], b[8 + k], b[12 + k], b[16 + k], b[20 + k], tmax[i])) m |= (uint8_t)(1u << k);
+  masks[i] = m;
+}
+
+int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir, double tmin, double tmax,
+                 int mode, int32_t* d_ids, double* d_t, cudaStream_t st, bool count) {
+  if (mode != IZPI_TRACE_EXACT) { set_error("izpi_trace_closest: only IZPI_TRACE_EXACT is implemented"); return IZPI_EINVAL; }
+  IZ_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(unsigned long long), st));
+  size_t smem = (size_t)kStackDepth * kTraceThreads * sizeof(int32_t);
+  auto kern = count ? trace_kernel<true> : trace_kernel<false>;
+  static thread_local int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    IZ_CUDA(cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IZ_CUDA(cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, trace_kernel<false>, kTraceThreads, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  long long want = (n + kTraceThreads - 1) / kTraceThreads;
+  long long grid = (long long)ctx->sm_count * blocks_per_sm;  // persistent: a whole number of waves
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, kTraceThreads, smem, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t,
+                                                     ctx->d_counters);
+  IZ_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return IZPI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int izpi_trace_closest_device(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir, double tmin, double tmax,
+                              int mode, int32_t* d_ids, double* d_t, void* stream) {
+  if (!ctx || n < 0) { set_error("izpi_trace_closest_device: bad argument"); return IZPI_EINVAL; }
+  if (!ctx->has_scene) { set_error("izpi_trace_closest_device: no scene uploaded"); return IZPI_ESTATE; }
+  if (n == 0) return IZPI_OK;
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  return launch_trace(ctx, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, stream ? (cudaStream_t)stream : ctx->stream, false);
+}
+
+int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double* dir, double tmin, double tmax, int mode,
+                       int32_t* prim_id, double* t, izpi_trace_stats* stats) {
+  if (!ctx || n < 0 || (n > 0 && (!org || !dir || !prim_id || !t))) { set_error("izpi_trace_closest: bad argument"); return IZPI_EINVAL; }
+  if (!ctx->has_scene) { set_error("izpi_trace_closest: no scene uploaded"); return IZPI_ESTATE; }
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return IZPI_OK;
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  if (n > ctx->ray_capacity) {
+    cudaFree(ctx->d_org); cudaFree(ctx->d_dir); cudaFree(ctx->d_ids); cudaFree(ctx->d_t);
+    ctx->d_org = ctx->d_dir = ctx->d_t = nullptr; ctx->d_ids = nullptr; ctx->ray_capacity = 0;
+    IZ_CUDA(cudaMalloc(&ctx->d_org, (size_t)n * 24));
+    IZ_CUDA(cudaMalloc(&ctx->d_dir, (size_t)n * 24));
+    IZ_CUDA(cudaMalloc(&ctx->d_ids, (size_t)n * 4));
+    IZ_CUDA(cudaMalloc(&ctx->d_t, (size_t)n * 8));
+    ctx->ray_capacity = n;
+  }
+  cudaStream_t st = ctx->stream;
+  // The batch is cut into slices so the copies of slice k+1 / k-1 overlap the traversal of slice k
+  // (pinned host buffers make the copies truly asynchronous; pageable ones still work).
+  const int64_t slice = 1 << 20;
+  IZ_CUDA(cudaEventRecord(ctx->ev0, st));
+  for (int64_t b = 0; b < n; b += slice) {
+    int64_t m = n - b < slice ? n - b : slice;
+    IZ_CUDA(cudaMemcpyAsync(ctx->d_org + 3 * b, org + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, st));
+    IZ_CUDA(cudaMemcpyAsync(ctx->d_dir + 3 * b, dir + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, st));
+  }
+  int rc = launch_trace(ctx, n, ctx->d_org, ctx->d_dir, tmin, tmax, mode, ctx->d_ids, ctx->d_t, st, stats != nullptr);
+  if (rc != IZPI_OK) return rc;
+  IZ_CUDA(cudaEventRecord(ctx->ev1, st));
+  IZ_CUDA(cudaMemcpyAsync(prim_id, ctx->d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  IZ_CUDA(cudaMemcpyAsync(t, ctx->d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  IZ_CUDA(cudaStreamSynchronize(st));
+  if (stats) {
+    unsigned long long c[3];
+    IZ_CUDA(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    stats->rays = (uint64_t)n; stats->nodes_visited = c[1]; stats->prim_tests = c[2];
+    float ms = 0;
+    IZ_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    stats->kernel_ms = ms;  // includes the H2D copies queued ahead of the kernel
+  }
+  return IZPI_OK;
+}
+
+uint64_t izpi_launch_count(const izpi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int izpi_debug_ray_aabb4(izpi_ctx* ctx, int32_t n, const float* org, const float* inv, const float* bounds, const float* tmax,
+                         uint8_t* masks) {
+  if (!ctx || n <= 0 || !org || !inv || !bounds || !tmax || !masks) { set_error("izpi_debug_ray_aabb4: bad argument"); return IZPI_EINVAL; }
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  float *d_o, *d_i, *d_b, *d_t; uint8_t* d_m;
+  IZ_CUDA(cudaMalloc(&d_o, (size_t)n * 12)); IZ_CUDA(cudaMalloc(&d_i, (size_t)n * 12));
+  IZ_CUDA(cudaMalloc(&d_b, (size_t)n * 96)); IZ_CUDA(cudaMalloc(&d_t, (size_t)n * 4)); IZ_CUDA(cudaMalloc(&d_m, (size_t)n));
+  IZ_CUDA(cudaMemcpy(d_o, org, (size_t)n * 12, cudaMemcpyHostToDevice));
+  IZ_CUDA(cudaMemcpy(d_i, inv, (size_t)n * 12, cudaMemcpyHostToDevice));
+  IZ_CUDA(cudaMemcpy(d_b, bounds, (size_t)n * 96, cudaMemcpyHostToDevice));
+  IZ_CUDA(cudaMemcpy(d_t, tmax, (size_t)n * 4, cudaMemcpyHostToDevice));
+  box4_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, d_o, d_i, d_b, d_t, d_m);
+  IZ_CUDA(cudaGetLastError());
+  ctx->launches++;
+  IZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  IZ_CUDA(cudaMemcpy(masks, d_m, (size_t)n, cudaMemcpyDeviceToHost));
+  cudaFree(d_o); cudaFree(d_i); cudaFree(d_b); cudaFree(d_t); cudaFree(d_m);
+  return IZPI_OK;
+}
+
+}  // extern "C"

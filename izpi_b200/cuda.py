@@ -1,0 +1,218 @@
+"""ctypes binding of libizpi_cuda.so -- the Python twin of the cgo package `internal/cuda`
+(INTEGRATION.md).  Thin by design: every call maps 1:1 onto an entry point of
+include/izpi_cuda.h / include/izpi_host.h; errors become exceptions carrying izpi_last_error().
+
+There is no CPU fallback: if the library is missing or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .scene import NODE_DTYPE, SceneSpec, SceneSpecC
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libizpi_cuda.so")
+
+OK, EINVAL, ECUDA, ESTATE = 0, -1, -2, -3
+TRACE_EXACT, TRACE_FP32 = 0, 1
+SAMPLER_COLOUR, SAMPLER_SPECTRAL = 0, 1
+
+
+class IzpiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"izpi error {code}: {msg}")
+        self.code = code
+
+
+class TraceStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("kernel_ms", C.c_double)]
+
+
+class RenderConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
+                ("sampler", C.c_int32), ("sample_offset", C.c_int32), ("sample_count", C.c_int32), ("reserved", C.c_int32),
+                ("background", C.c_double * 3), ("bg_wavelengths", C.c_void_p), ("bg_values", C.c_void_p),
+                ("n_bg", C.c_int32), ("reserved2", C.c_int32), ("seed", C.c_uint64)]
+
+
+# every symbol include/izpi_cuda.h and include/izpi_host.h declare (checked by tests/test_abi.py)
+EXPORTS = [
+    "izpi_last_error", "izpi_version", "izpi_ctx_create", "izpi_ctx_destroy", "izpi_scene_upload",
+    "izpi_trace_closest", "izpi_trace_closest_device", "izpi_launch_count", "izpi_render_setup", "izpi_render_tiles",
+    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4",
+    "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
+    "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
+    "izpi_host_tiles", "izpi_host_render",
+]
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (built in-tree by izpi_b200/build.py).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IzpiError(ECUDA, f"{LIB_PATH} is missing: run `python -m izpi_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    L.izpi_last_error.restype = C.c_char_p
+    L.izpi_version.restype = C.c_int
+    L.izpi_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    L.izpi_ctx_destroy.argtypes = [C.c_void_p]
+    L.izpi_ctx_destroy.restype = None
+    L.izpi_scene_upload.argtypes = [C.c_void_p, C.c_void_p]
+    L.izpi_trace_closest.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.POINTER(TraceStats)]
+    L.izpi_trace_closest_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+    L.izpi_launch_count.argtypes = [C.c_void_p]
+    L.izpi_launch_count.restype = C.c_uint64
+    L.izpi_debug_ray_aabb4.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.izpi_render_setup.argtypes = [C.c_void_p, C.POINTER(RenderConfig)]
+    L.izpi_render_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.izpi_render_canvas_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.izpi_render_finish.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.izpi_host_scene_create.argtypes = [C.POINTER(SceneSpecC), C.c_int, C.POINTER(C.c_void_p)]
+    L.izpi_host_scene_destroy.argtypes = [C.c_void_p]
+    L.izpi_host_scene_destroy.restype = None
+    L.izpi_host_scene_num_nodes.argtypes = [C.c_void_p]
+    L.izpi_host_scene_num_nodes.restype = C.c_int32
+    L.izpi_host_scene_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.izpi_host_scene_num_lights.argtypes = [C.c_void_p]
+    L.izpi_host_scene_num_lights.restype = C.c_int32
+    L.izpi_host_scene_lights.argtypes = [C.c_void_p, C.c_void_p]
+    L.izpi_host_scene_desc.argtypes = [C.c_void_p, C.c_void_p]
+    L.izpi_host_scene_upload.argtypes = [C.c_void_p, C.c_void_p]
+    L.izpi_host_tiles.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.izpi_host_tiles.restype = None
+    L.izpi_host_render.argtypes = [C.c_void_p, C.POINTER(RenderConfig), C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != OK:
+        raise IzpiError(rc, lib().izpi_last_error().decode("utf-8", "replace"))
+
+
+def tiles(size_x: int, size_y: int):
+    """common.Tiles (common/tiles.go:6-24)."""
+    a, b = C.c_int32(), C.c_int32()
+    lib().izpi_host_tiles(size_x, size_y, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+class HostScene:
+    """scene.Scene as built by the host runtime (izpi_host_scene_create)."""
+
+    def __init__(self, spec: SceneSpec, threads: int | None = None):
+        self._spec = spec
+        self._c = spec.to_c()
+        h = C.c_void_p()
+        check(lib().izpi_host_scene_create(C.byref(self._c), threads or os.cpu_count() or 1, C.byref(h)))
+        self._h = h
+        self.n_prims = self._c.n_prims
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().izpi_host_scene_destroy(self._h)
+            self._h = None
+
+    def bvh(self):
+        """(BVH4.Nodes, permutation) -- exported fields of hitable.BVH4 (bvh4.go:42-47)."""
+        n = lib().izpi_host_scene_num_nodes(self._h)
+        nodes = np.zeros(n, dtype=NODE_DTYPE)
+        perm = np.zeros(self.n_prims if n else 0, dtype=np.int32)
+        check(lib().izpi_host_scene_bvh(self._h, nodes.ctypes.data, perm.ctypes.data))
+        return nodes, perm
+
+    def lights(self):
+        n = lib().izpi_host_scene_num_lights(self._h)
+        ids = np.zeros(n, dtype=np.int32)
+        if n:
+            check(lib().izpi_host_scene_lights(self._h, ids.ctypes.data))
+        return ids
+
+
+class Context:
+    """One GPU (izpi_ctx)."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        ids = (C.c_int * 1)(device)
+        check(lib().izpi_ctx_create(1, ids, C.byref(h)))
+        self._h = h
+        self.device = device
+        self._scene = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().izpi_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def upload(self, scene: HostScene):
+        check(lib().izpi_host_scene_upload(scene._h, self._h))
+        self._scene = scene
+
+    @property
+    def launches(self) -> int:
+        return int(lib().izpi_launch_count(self._h))
+
+    # ---- hitable.Hitable.Hit, batched -------------------------------------------------------
+    def trace_closest(self, org, direction, tmin=0.001, tmax=np.finfo(np.float64).max, mode=TRACE_EXACT, stats=False,
+                      out_ids=None, out_t=None):
+        o = np.ascontiguousarray(org, dtype=np.float64)
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        n = o.shape[0] if o.ndim == 2 else 0
+        if o.shape != d.shape or (n and o.shape[1] != 3):
+            raise IzpiError(EINVAL, "org/dir must both be (n, 3)")
+        ids = out_ids if out_ids is not None else np.empty(n, dtype=np.int32)
+        t = out_t if out_t is not None else np.empty(n, dtype=np.float64)
+        st = TraceStats()
+        check(lib().izpi_trace_closest(self._h, n, o.ctypes.data, d.ctypes.data, tmin, tmax, mode, ids.ctypes.data,
+                                       t.ctypes.data, C.byref(st) if stats else None))
+        if stats:
+            return ids, t, dict(rays=st.rays, nodes=st.nodes_visited, prims=st.prim_tests, kernel_ms=st.kernel_ms)
+        return ids, t
+
+    def trace_closest_device(self, n, d_org, d_dir, d_ids, d_t, tmin=0.001, tmax=np.finfo(np.float64).max,
+                             mode=TRACE_EXACT, stream=0):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on `stream`."""
+        check(lib().izpi_trace_closest_device(self._h, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, stream or None))
+
+    def debug_ray_aabb4(self, org, inv, bounds, tmax):
+        o = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)
+        i = np.ascontiguousarray(inv, dtype=np.float32).reshape(-1, 3)
+        b = np.ascontiguousarray(bounds, dtype=np.float32).reshape(-1, 24)
+        t = np.ascontiguousarray(tmax, dtype=np.float32).reshape(-1)
+        m = np.zeros(len(o), dtype=np.uint8)
+        check(lib().izpi_debug_ray_aabb4(self._h, len(o), o.ctypes.data, i.ctypes.data, b.ctypes.data, t.ctypes.data, m.ctypes.data))
+        return m
+
+    # ---- render.New(...).Render() ------------------------------------------------------------
+    def render(self, width, height, spp, max_depth=50, sampler=SAMPLER_COLOUR, seed=1, sample_offset=0, sample_count=None,
+               tile_begin=0, tile_end=-1, finish=True):
+        cfg = RenderConfig(width=width, height=height, spp=spp, max_depth=max_depth, sampler=sampler,
+                           sample_offset=sample_offset, sample_count=spp if sample_count is None else sample_count, seed=seed)
+        canvas = np.zeros((height, width, 4), dtype=np.float64)
+        rays = C.c_uint64()
+        check(lib().izpi_host_render(self._h, C.byref(cfg), tile_begin, tile_end, int(finish), canvas.ctypes.data, C.byref(rays)))
+        return canvas, rays.value
+
+    def canvas_device_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib().izpi_render_canvas_device(self._h, C.byref(p)))
+        return p.value
+
+    def render_finish(self, width, height):
+        canvas = np.zeros((height, width, 4), dtype=np.float64)
+        rays = C.c_uint64()
+        check(lib().izpi_render_finish(self._h, canvas.ctypes.data, C.byref(rays)))
+        return canvas, rays.value

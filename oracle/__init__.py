@@ -112,7 +112,7 @@ class OracleScene:
     def bvh(self):
         n = lib().oracle_scene_num_nodes(self._h)
         nodes = np.zeros(n, dtype=NODE_DTYPE)
-        perm = np.zeros(self._c.n_prims, dtype=np.int32)
+        perm = np.zeros(self._c.n_prims if n else 0, dtype=np.int32)
         lib().oracle_scene_bvh(self._h, nodes.ctypes.data, perm.ctypes.data)
         return nodes, perm
 

@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares; without a GPU every
+compute entry point fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from izpi_b200 import cuda
+from izpi_b200.build import build as build_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    build_lib()
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(izpi_[a-z0-9_]+)\s*\(", src))
+
+
+def test_exports_match_headers():
+    declared = _declared("izpi_cuda.h") | _declared("izpi_host.h")
+    assert declared == set(cuda.EXPORTS)
+    L = C.CDLL(cuda.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_struct_sizes_match_header():
+    from izpi_b200 import scene as S
+    assert S.PRIM_DTYPE.itemsize == 168 and S.NODE_DTYPE.itemsize == 128
+    assert C.sizeof(S.MaterialSpec) == 64 and C.sizeof(S.TextureSpec) == 48 and C.sizeof(S.CameraSpec) == 128
+    assert C.sizeof(cuda.RenderConfig) == 88 and C.sizeof(cuda.TraceStats) == 32
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(cuda.IzpiError) as e:
+        cuda.Context(0)
+    assert e.value.code == cuda.ECUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_null_arguments_rejected():
+    L = cuda.lib()
+    assert L.izpi_ctx_create(1, None, None) == cuda.EINVAL
+    assert L.izpi_scene_upload(None, None) == cuda.EINVAL
+    assert L.izpi_trace_closest(None, 1, None, None, 0.0, 1.0, 0, None, None, None) == cuda.EINVAL
+    assert b"bad argument" in L.izpi_last_error()
