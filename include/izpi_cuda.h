@@ -69,11 +69,14 @@ typedef struct izpi_prim_rec {
 #define IZPI_TAG(type, flip, material, xform1) \
   ((uint32_t)(type) | ((uint32_t)((flip) ? 1 : 0) << 3) | ((uint32_t)(material) << 4) | ((uint32_t)(xform1) << 18))
 
-/* Shading attributes of a triangle, same index as its record (triangle.go:35-50). 128 bytes. */
+/* Shading attributes of a triangle, same index as its record (triangle.go:20-50). 176 bytes.
+ * vertex1/vertex2 are kept exactly because Triangle.Random (triangle.go:317-326) lerps between
+ * the original vertices. */
 typedef struct izpi_tri_attr {
   double normal[3], tangent[3], bitangent[3];
   double uv[6]; /* u0 v0 u1 v1 u2 v2 */
   double area;
+  double vertex1[3], vertex2[3];
 } izpi_tri_attr;
 
 /* Translate(RotateY(.)) wrapper chain (translate.go:16-19, rotate_y.go:19-25). */

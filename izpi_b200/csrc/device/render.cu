@@ -1,14 +1,704 @@
-// render.cu -- tile rendering entry points (placeholder until the wavefront kernels land).
-#include "dscene.cuh"
+// render.cu -- wavefront path tracer behind the tile seam (renderRectRGB render/rgb.go:12,
+// renderRectSpectral render/spectral.go:14, worker.RenderTile worker/render.go:17).
+//
+// One path = one (pixel, sample).  A batch of paths lives in HBM as 160-byte PathState records;
+// each bounce runs
+//   extend_kernel   closest hit for every live path (persistent warps, the trace kernel's traversal),
+//                   misses terminate, hits are binned BY MATERIAL CLASS with warp match/ballot/popc
+//                   prefix ranks and one atomicAdd per (warp, class);
+//   shade_kernel<C> one launch per class over its bin: emission, BSDF sampling, light/BSDF mixture PDF
+//                   (sampler/colour.go:33-65, sampler/spectral.go:47-80 in iterative form), survivors
+//                   are compacted into the next bounce's queue the same way;
+// then resolve_kernel sums each pixel's samples in sample order (the reference's loop order,
+// rgb.go:30-39) into the fp64 canvas.  All arithmetic is fp64 without FMA.
+#include <algorithm>
+#include <cstring>
+
+#include "shade.cuh"
 
 using namespace izpi;
 
-struct RenderState {};
-void render_state_free(izpi_ctx* ctx) { delete ctx->render; ctx->render = nullptr; }
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kStackDepth = 64;
+constexpr int kClasses = 5;  // IZPI_MAT_* types
+
+struct alignas(16) PathState {
+  double ox, oy, oz, dx, dy, dz, time, lambda;  // ray.RayImpl
+  double bx, by, bz;                            // throughput (spectral: bx)
+  double ax, ay, az;                            // accumulated radiance / final sample value
+  double hit_t, lpdf;                           // closest hit t; wavelength pdf (spectral)
+  uint64_t key;                                 // RNG stream key
+  uint32_t ctr;                                 // RNG draw counter
+  int32_t depth;
+  int32_t hit_rec;
+  int32_t alive;
+  int32_t pad0, pad1;
+};
+static_assert(sizeof(PathState) == 160, "PathState layout");
+
+struct RenderParams {
+  int32_t width, height, spp, max_depth, sampler;
+  int32_t n_bg;
+  double background[3];
+  const double* bg_w;
+  const double* bg_v;
+  uint64_t seed;
+};
+
+struct Queues {
+  int32_t* cur;                 // live paths entering this bounce
+  int32_t* next;                // survivors
+  int32_t* bins;                // [kClasses][capacity]
+  unsigned long long* counters; // [0] cur count, [1] next count, [2..6] bin counts, [7] work head, [8] rays traced
+  int32_t capacity;
+};
+
+__device__ __forceinline__ DRay path_ray(const PathState& p) {
+  DRay r;
+  r.o = mk(p.ox, p.oy, p.oz); r.d = mk(p.dx, p.dy, p.dz); r.time = p.time; r.lambda = p.lambda;
+  return r;
+}
+
+// Warp-aggregated append: lanes with `want` and the same `cls` share one atomicAdd.
+__device__ __forceinline__ void push_binned(bool want, int cls, int32_t value, int32_t* base, int stride,
+                                            unsigned long long* counts) {
+  unsigned active = __ballot_sync(0xffffffffu, want);
+  if (!want) return;
+  unsigned peers = __match_any_sync(active, cls);
+  int leader = __ffs(peers) - 1;
+  unsigned lane = threadIdx.x & 31u;
+  unsigned long long slot = 0;
+  if ((int)lane == leader) slot = atomicAdd(&counts[cls], (unsigned long long)__popc(peers));
+  slot = __shfl_sync(peers, slot, leader);
+  int rank = __popc(peers & ((1u << lane) - 1u));
+  base[(size_t)cls * stride + slot + rank] = value;
+}
+
+// ---- ray generation -------------------------------------------------------------------------
+// path index = pixel_local * s_count + s.  Draw order per sample (rgb.go:31-36 / render/spectral.go:77-88):
+// [lambda] u v, camera disc (rejection), camera time.
+__global__ void raygen_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths,
+                              const uint32_t* __restrict__ pixels, int n_pixels, int s_begin, int s_count, Queues q) {
+  long long n = (long long)n_pixels * s_count;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int pl = (int)(i / s_count), s = s_begin + (int)(i % s_count);
+    uint32_t xy = pixels[pl];
+    int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+    PathState p;
+    Rng rng;
+    rng.key = stream_key(rp.seed, (uint64_t)y * (uint64_t)rp.width + (uint64_t)x, (uint64_t)s);
+    rng.ctr = 0;
+    double lambda = 0, lpdf = 1;
+    bool live = true;
+    if (rp.sampler == IZPI_SAMPLER_SPECTRAL) {
+      sample_wavelength(rnd(rng), lambda, lpdf);
+      if (lpdf == 0) live = false;  // `continue` in RenderPixelSpectral (spectral.go:80-82)
+    }
+    const izpi_camera& c = sc.camera;
+    if (live) {
+      double u = ((double)x + rnd(rng)) / (double)rp.width;
+      double v = ((double)y + rnd(rng)) / (double)rp.height;
+      d3 disc;
+      for (;;) {  // camera.randomInUnitDisc (camera.go:82-89)
+        double a = rnd(rng);
+        double b = rnd(rng);
+        disc = mk(a, b, 0) * 2.0 - mk(1.0, 1.0, 0);
+        if (dot(disc, disc) < 1.0) break;
+      }
+      d3 rd = disc * c.lens_radius;
+      d3 cu = mk(c.u[0], c.u[1], c.u[2]), cv = mk(c.v[0], c.v[1], c.v[2]);
+      d3 offset = cu * rd.x + cv * rd.y;
+      double time = c.time0 + rnd(rng) * (c.time1 - c.time0);
+      d3 org = mk(c.origin[0], c.origin[1], c.origin[2]);
+      d3 llc = mk(c.lower_left_corner[0], c.lower_left_corner[1], c.lower_left_corner[2]);
+      d3 hor = mk(c.horizontal[0], c.horizontal[1], c.horizontal[2]), ver = mk(c.vertical[0], c.vertical[1], c.vertical[2]);
+      d3 dir = (((llc + hor * u) + ver * v) - org) - offset;  // camera.go:66-69
+      d3 o = org + offset;
+      p.ox = o.x; p.oy = o.y; p.oz = o.z; p.dx = dir.x; p.dy = dir.y; p.dz = dir.z; p.time = time;
+    } else {
+      p.ox = p.oy = p.oz = p.dx = p.dy = p.dz = p.time = 0;
+    }
+    p.lambda = lambda; p.lpdf = lpdf;
+    p.bx = p.by = p.bz = 1.0;
+    p.ax = p.ay = p.az = 0.0;
+    p.hit_t = 0; p.key = rng.key; p.ctr = rng.ctr; p.depth = 0; p.hit_rec = -1; p.alive = live ? 1 : 0;
+    p.pad0 = p.pad1 = 0;
+    paths[i] = p;
+    // every live path enters bounce 0; the queue is the identity (dead spectral samples are skipped)
+    unsigned m = __ballot_sync(__activemask(), live);
+    if (live) {
+      unsigned lane = threadIdx.x & 31u;
+      int leader = __ffs(m) - 1;
+      unsigned long long slot = 0;
+      if ((int)lane == leader) slot = atomicAdd(&q.counters[0], (unsigned long long)__popc(m));
+      slot = __shfl_sync(m, slot, leader);
+      q.cur[slot + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+    }
+  }
+}
+
+// terminal value of a path: what the pixel loop adds for this sample
+__device__ __forceinline__ void finish_path(const RenderParams& rp, PathState& p, d3 acc) {
+  if (rp.sampler == IZPI_SAMPLER_COLOUR) {  // vec3.DeNAN (rgb.go:36, vec3.go:141-158)
+    p.ax = isfinite(acc.x) ? acc.x : 0.0; p.ay = isfinite(acc.y) ? acc.y : 0.0; p.az = isfinite(acc.z) ? acc.z : 0.0;
+  } else {  // render/spectral.go:91-95: XYZ += radiance * cmf / pdf, no DeNAN
+    d3 cmf = cie_values(p.lambda);
+    p.ax = (acc.x * cmf.x) / p.lpdf; p.ay = (acc.x * cmf.y) / p.lpdf; p.az = (acc.x * cmf.z) / p.lpdf;
+  }
+  p.alive = 0;
+}
+
+__device__ __forceinline__ d3 background_term(const RenderParams& rp, double lambda) {
+  if (rp.sampler == IZPI_SAMPLER_COLOUR) return mk(rp.background[0], rp.background[1], rp.background[2]);
+  double v = rp.n_bg > 0 ? spd_value(rp.bg_w, rp.bg_v, rp.n_bg, lambda) : 0.0;  // colours.SpectralBlack
+  return mk(v, 0, 0);
+}
+
+// ---- extend ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q) {
+  extern __shared__ int32_t stack_smem[];
+  int32_t* stack = stack_smem + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  const long long n = (long long)q.counters[0];
+  uint32_t nn = 0, np = 0;
+  unsigned long long traced = 0;
+  for (;;) {
+    long long base = 0;
+    if (lane == 0) base = (long long)atomicAdd(&q.counters[7], 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    long long i = base + lane;
+    bool hit = false;
+    int cls = 0;
+    int32_t pi = -1;
+    if (i < n) {
+      pi = q.cur[i];
+      PathState& p = paths[pi];
+      if (p.depth >= rp.max_depth) {
+        // colour.go:34-36 returns (0,0,1); spectral.go:48-51 returns the background SPD
+        d3 term = rp.sampler == IZPI_SAMPLER_COLOUR ? mk(0, 0, 1.0) : background_term(rp, p.lambda);
+        d3 beta = mk(p.bx, p.by, p.bz), acc = mk(p.ax, p.ay, p.az);
+        finish_path(rp, p, acc + hadamard(beta, term));
+      } else {
+        traced++;  // atomic.AddUint64(numRays, 1) (colour.go:38)
+        DRay r = path_ray(p);
+        double t = 0;
+        int rec = world_closest<false>(sc, r, 0.001, DBL_MAX, t, stack, kThreads, nn, np);
+        if (rec < 0) {
+          d3 beta = mk(p.bx, p.by, p.bz), acc = mk(p.ax, p.ay, p.az);
+          finish_path(rp, p, acc + hadamard(beta, background_term(rp, p.lambda)));
+        } else {
+          p.hit_rec = rec; p.hit_t = t;
+          hit = true;
+          cls = sc.materials[tag_material(sc.prims[rec].tag)].type;
+        }
+      }
+    }
+    __syncwarp();
+    push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + 2);
+  }
+  if (traced) atomicAdd(&q.counters[8], traced);
+}
+
+// ---- shade ----------------------------------------------------------------------------------
+// Dielectric.calculatePathLength (dielectric.go:119-153): nested closest hit from just inside the surface.
+__device__ __noinline__ double path_length(const DScene& sc, d3 hit_p, d3 sdir, double time, double lambda) {
+  if (!sc.dielectric_has_world) return 10.0;
+  DRay tr;
+  tr.o = hit_p + sdir * 0.001; tr.d = sdir; tr.time = time; tr.lambda = lambda;
+  int32_t stack[kStackDepth];
+  uint32_t a = 0, b = 0;
+  double t = 0;
+  int rec = world_closest<false>(sc, tr, 0.0, 1000.0, t, stack, 1, a, b);
+  if (rec < 0) return 10.0;
+  PrimRec pr = load_rec(sc.prims + rec);
+  DHit eh;
+  prim_hit<true>(sc, rec, pr, tr, 0.0, DBL_MAX, eh);
+  double pl = len(eh.p - hit_p);
+  if (pl < 0.1) pl = 0.1;
+  if (pl > 100.0) pl = 100.0;
+  return pl;
+}
+
+struct Scatter {
+  bool ok, specular;
+  d3 spec_dir;     // SpecularRay direction (origin = hit point)
+  d3 atten;        // RGB attenuation, or (a,0,0) spectral
+  d3 pdf_w;        // W axis of the Cosine pdf (already unit)
+};
+
+// pbr.go:59-156 / :158-263, the part shared by the RGB and the spectral scatter
+__device__ __forceinline__ void pbr_common(const DScene& sc, const izpi_material_spec& m, const DRay& r, const DHit& h,
+                                           Rng& rng, Scatter& s) {
+  d3 normal;
+  if (m.normal_tex >= 0) {
+    d3 nuv = texture_value(sc, m.normal_tex, h.u, h.v);
+    d3 tn = mk(2.0 * nuv.x - 1.0, 2.0 * nuv.y - 1.0, nuv.z);
+    d3 n = h.n;
+    d3 t = cross(n, mk(0, 1, 0));
+    if (dot(t, t) < 0.001) t = cross(n, mk(1, 0, 0));
+    t = unit(t);
+    d3 b = unit(cross(n, t));
+    normal = unit(mk(t.x * tn.x + b.x * tn.y + n.x * tn.z, t.y * tn.x + b.y * tn.y + n.y * tn.z,
+                     t.z * tn.x + b.z * tn.y + n.z * tn.z));
+  } else {
+    normal = h.n;
+  }
+  d3 rough = m.roughness_tex >= 0 ? texture_value(sc, m.roughness_tex, h.u, h.v) : mk(0.5, 0.5, 0.5);
+  d3 metal = m.metalness_tex >= 0 ? texture_value(sc, m.metalness_tex, h.u, h.v) : mk(0, 0, 0);
+  double roughness = (rough.x + rough.y + rough.z) / 3.0;
+  double metalness = (metal.x + metal.y + metal.z) / 3.0;
+  Onb uvw = onb_from_w(normal);
+  d3 ud = unit(r.d);
+  d3 reflected = reflect(ud, normal);
+  double cos_theta = fabs(dot(ud, normal));
+  double fresnel = 0.04 + (1.0 - 0.04) * pow(1.0 - cos_theta, 5.0);
+  fresnel = fresnel + (metalness * 0.5);
+  double p_spec = fresnel * (1.0 - roughness);
+  if (rnd(rng) < p_spec) {
+    double rf = roughness * 0.3;
+    if (!(0.01 < rf)) rf = 0.01;  // math.Max(0.01, rf)
+    d3 rdir = random_in_unit_sphere(rng);
+    s.spec_dir = unit(reflected + rdir * rf);
+    s.specular = true;
+  } else {
+    (void)unit(onb_local(uvw, random_cosine_direction(rng)));  // finalDir: drawn, then ignored by the integrator
+    s.specular = false;
+  }
+  s.pdf_w = uvw.w;
+  s.ok = true;
+}
+
+// dielectric.go:66-102
+__device__ __forceinline__ d3 dielectric_common(const DRay& r, const DHit& h, Rng& rng, double ref_idx, bool& reflected_out) {
+  d3 outward;
+  double ni_over_nt, cosine, reflect_prob;
+  d3 reflected = reflect(r.d, h.n);
+  double dn = dot(r.d, h.n);
+  if (dn > 0) {
+    outward = h.n * -1.0;
+    ni_over_nt = ref_idx;
+    cosine = ref_idx * dn / len(r.d);
+  } else {
+    outward = h.n;
+    ni_over_nt = 1.0 / ref_idx;
+    cosine = -dn / len(r.d);
+  }
+  d3 refracted = mk(0, 0, 0);
+  if (refract(r.d, outward, ni_over_nt, refracted)) reflect_prob = schlick(cosine, ref_idx);
+  else reflect_prob = 1.0;
+  if (rnd(rng) < reflect_prob) { reflected_out = true; return reflected; }
+  reflected_out = false;
+  return refracted;
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(kThreads)
+shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q) {
+  const long long n = (long long)q.counters[2 + CLS];
+  const int32_t* bin = q.bins + (size_t)CLS * q.capacity;
+  const bool spectral = rp.sampler == IZPI_SAMPLER_SPECTRAL;
+  const long long n_round = (n + 31) & ~31ll;  // whole warps stay in the loop for the ballots
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_round; i += (long long)gridDim.x * blockDim.x) {
+    bool survive = false;
+    int32_t pi = -1;
+    if (i < n) {
+      pi = bin[i];
+      PathState& p = paths[pi];
+      DRay r = path_ray(p);
+      PrimRec pr = load_rec(sc.prims + p.hit_rec);
+      const izpi_material_spec& m = sc.materials[tag_material(pr.tag)];
+      DHit h;
+      prim_hit<true>(sc, p.hit_rec, pr, r, 0.001, DBL_MAX, h);
+      h.t = p.hit_t;
+      Rng rng;
+      rng.key = p.key; rng.ctr = p.ctr;
+      d3 beta = mk(p.bx, p.by, p.bz), acc = mk(p.ax, p.ay, p.az);
+      Scatter s;
+      s.ok = false; s.specular = false; s.spec_dir = mk(0, 0, 0); s.atten = mk(0, 0, 0); s.pdf_w = mk(0, 0, 1);
+      d3 emitted = mk(0, 0, 0);
+      if (CLS == IZPI_MAT_LAMBERT) {  // lambertian.go:44-71
+        Onb uvw = onb_from_w(h.n);
+        (void)onb_local(uvw, random_cosine_direction(rng));  // scatterCommon's ray: two draws, result unused
+        s.pdf_w = uvw.w; s.ok = true; s.specular = false;
+        if (spectral) s.atten = mk(m.spectral_tex >= 0 ? spectral_value(sc, m.spectral_tex, p.lambda) : 0.0, 0, 0);
+        else s.atten = m.tex >= 0 ? texture_value(sc, m.tex, h.u, h.v) : mk(0, 0, 0);
+      } else if (CLS == IZPI_MAT_METAL) {  // metal.go:34-41; spectral: non_spectral.go:18-20 -> no scatter
+        if (!spectral) {
+          d3 reflected = reflect(unit(r.d), h.n);
+          s.spec_dir = reflected + random_in_unit_sphere(rng) * m.s;
+          s.atten = mk(m.v[0], m.v[1], m.v[2]);
+          s.ok = true; s.specular = true;
+        }
+      } else if (CLS == IZPI_MAT_DIELECTRIC) {  // dielectric.go:156-207
+        double ref_idx = spectral ? spectral_value(sc, m.spectral_tex, p.lambda) : m.s;
+        bool is_reflected;
+        s.spec_dir = dielectric_common(r, h, rng, ref_idx, is_reflected);
+        s.ok = true; s.specular = true;
+        if (spectral) {
+          double albedo = 1.0;
+          if (!is_reflected) {
+            double pl = path_length(sc, h.p, s.spec_dir, r.time, p.lambda);
+            if (m.spectral_absorption_tex >= 0) albedo = exp(-spectral_value(sc, m.spectral_absorption_tex, p.lambda) * pl);
+          }
+          s.atten = mk(albedo, 0, 0);
+        } else if (m.compute_beer_lambert && !(m.v[0] == 0 && m.v[1] == 0 && m.v[2] == 0) && !is_reflected) {
+          double pl = path_length(sc, h.p, s.spec_dir, r.time, p.lambda);
+          s.atten = mk(exp(-m.v[0] * pl), exp(-m.v[1] * pl), exp(-m.v[2] * pl));
+        } else {
+          s.atten = mk(1.0, 1.0, 1.0);
+        }
+      } else if (CLS == IZPI_MAT_DIFFUSE_LIGHT) {  // diffuselight.go:41-63
+        if (dot(h.n, r.d) < 0.0) {
+          if (spectral) emitted = mk(m.spectral_tex >= 0 ? spectral_value(sc, m.spectral_tex, p.lambda) : 0.0, 0, 0);
+          else emitted = m.tex >= 0 ? texture_value(sc, m.tex, h.u, h.v) : mk(0, 0, 0);
+        }
+      } else {  // PBR
+        if (spectral) {
+          double albedo;
+          if (m.spectral_tex >= 0) albedo = spectral_value(sc, m.spectral_tex, p.lambda);
+          else { d3 rgb = texture_value(sc, m.tex, h.u, h.v); albedo = 0.299 * rgb.x + 0.587 * rgb.y + 0.114 * rgb.z; }
+          pbr_common(sc, m, r, h, rng, s);
+          s.atten = mk(s.specular ? albedo * 1.5 : albedo, 0, 0);
+        } else {
+          d3 albedo = texture_value(sc, m.tex, h.u, h.v);
+          pbr_common(sc, m, r, h, rng, s);
+          s.atten = albedo;
+        }
+      }
+
+      // the integrator step (colour.go:41-61 / spectral.go:57-76) in iterative form:
+      //   L = E + atten * L' * scatPDF / pdf   ->   acc += beta*E ; beta *= atten*scatPDF/pdf
+      if (!s.ok) {
+        finish_path(rp, p, acc + hadamard(beta, emitted));
+      } else if (s.specular) {  // emitted is dropped on the specular branch
+        beta = hadamard(beta, s.atten);
+        p.ox = h.p.x; p.oy = h.p.y; p.oz = h.p.z; p.dx = s.spec_dir.x; p.dy = s.spec_dir.y; p.dz = s.spec_dir.z;
+        survive = true;
+      } else {
+        d3 dir = rnd(rng) < 0.5 ? lights_random(sc, h.p, rng) : onb_local(onb_from_w(s.pdf_w), random_cosine_direction(rng));
+        double pdf_val = 0.5 * lights_pdf_value(sc, h.p, dir) + 0.5 * cosine_pdf_value(s.pdf_w, dir);
+        double cosine = dot(h.n, unit(dir));  // ScatteringPDF (lambertian.go:74-81, pbr.go:266-273)
+        if (cosine < 0) cosine = 0;
+        double spdf = cosine / M_PI;
+        acc = acc + hadamard(beta, emitted);
+        if (spectral) beta.x = beta.x * ((s.atten.x * spdf) / pdf_val);
+        else beta = hadamard(beta, (s.atten * spdf) / pdf_val);
+        p.ox = h.p.x; p.oy = h.p.y; p.oz = h.p.z; p.dx = dir.x; p.dy = dir.y; p.dz = dir.z;
+        survive = true;
+      }
+      if (survive) {
+        p.bx = beta.x; p.by = beta.y; p.bz = beta.z; p.ax = acc.x; p.ay = acc.y; p.az = acc.z;
+        p.key = rng.key; p.ctr = rng.ctr; p.depth = p.depth + 1;
+      }
+    }
+    push_binned(survive, 0, pi, q.next, q.capacity, q.counters + 1);
+  }
+}
+
+// swap queues between bounces without a host round trip
+__global__ void advance_kernel(Queues q, unsigned long long* host_visible_count) {
+  q.counters[0] = q.counters[1];
+  *host_visible_count = q.counters[1];
+  q.counters[1] = 0;
+  for (int c = 0; c < kClasses; c++) q.counters[2 + c] = 0;
+  q.counters[7] = 0;
+}
+
+// ---- resolve ----------------------------------------------------------------------------------
+// canvas holds running per-pixel SUMS (rgb.go:30-37 adds sample after sample); the row is ny - y and
+// y == 0 falls outside the image (rgb.go:41; floatimage drops out-of-bounds Set calls).
+__global__ void resolve_kernel(RenderParams rp, const PathState* __restrict__ paths, const uint32_t* __restrict__ pixels,
+                               int n_pixels, int s_count, double* canvas) {
+  int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= n_pixels) return;
+  uint32_t xy = pixels[pl];
+  int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+  int row = rp.height - y;
+  if (row < 0 || row >= rp.height) return;
+  double* px = canvas + ((size_t)row * rp.width + x) * 4;
+  double a = px[0], b = px[1], c = px[2];
+  const PathState* p = paths + (size_t)pl * s_count;
+  for (int s = 0; s < s_count; s++) { a = a + p[s].ax; b = b + p[s].ay; c = c + p[s].az; }
+  px[0] = a; px[1] = b; px[2] = c; px[3] = 1.0;
+}
+
+// mean over spp: RGB divides (rgb.go:39), spectral multiplies by 1/spp (render/spectral.go:99-103)
+__global__ void mean_kernel(RenderParams rp, const double* __restrict__ sums, double* __restrict__ out, long long n_px) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  double a = sums[4 * i], b = sums[4 * i + 1], c = sums[4 * i + 2];
+  if (rp.sampler == IZPI_SAMPLER_COLOUR) { a = a / (double)rp.spp; b = b / (double)rp.spp; c = c / (double)rp.spp; }
+  else { double inv = 1.0 / (double)rp.spp; a = a * inv; b = b * inv; c = c * inv; }
+  out[4 * i] = a; out[4 * i + 1] = b; out[4 * i + 2] = c; out[4 * i + 3] = sums[4 * i + 3];
+}
+
+// spectral.FireflyRejection (firefly_rejection.go:12-113): 3x3 neighbourhood of a SNAPSHOT of Y
+__global__ void firefly_kernel(const double* __restrict__ snap, double* __restrict__ pix, int width, int height) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= width || y >= height) return;
+  size_t idx = ((size_t)y * width + x) * 4;
+  double cur = snap[idx + 1];
+  if (cur <= 0) return;
+  double nb[8];
+  int n = 0;
+  for (int dy = -1; dy <= 1; dy++)
+    for (int dx = -1; dx <= 1; dx++) {
+      if (dx == 0 && dy == 0) continue;
+      int nx = x + dx, ny = y + dy;
+      if (nx >= 0 && nx < width && ny >= 0 && ny < height) {
+        double v = snap[((size_t)ny * width + nx) * 4 + 1];
+        if (v > 0) nb[n++] = v;
+      }
+    }
+  if (n < 3) return;
+  double sum = 0.0;
+  for (int i = 0; i < n; i++) sum += nb[i];
+  double mean = sum / (double)n;
+  double var = 0.0;
+  for (int i = 0; i < n; i++) { double d = nb[i] - mean; var += d * d; }
+  double stddev = sqrt(var / (double)n);
+  double threshold = mean + 2.5 * stddev;
+  if (cur > threshold && threshold > 0) {
+    double ratio = threshold / cur;
+    pix[idx] *= ratio; pix[idx + 1] *= ratio; pix[idx + 2] *= ratio;
+  }
+}
+
+// spectral.XYZToRGB (rgb_image.go:13-17,28-67)
+__global__ void xyz_to_acescg_kernel(double* pix, long long n_px, double exposure) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  double x = pix[4 * i] * exposure, y = pix[4 * i + 1] * exposure, z = pix[4 * i + 2] * exposure;
+  pix[4 * i] = 1.6410234 * x + -0.3248033 * y + -0.2364247 * z;
+  pix[4 * i + 1] = -0.6636629 * x + 1.6153316 * y + 0.0167563 * z;
+  pix[4 * i + 2] = 0.0117219 * x + -0.0082845 * y + 0.9883949 * z;
+}
+
+}  // namespace
+
+// ---- host side of the render entry points -------------------------------------------------------
+struct RenderState {
+  izpi_render_config cfg{};
+  RenderParams rp{};
+  double* d_canvas = nullptr;   // running sums, 4*W*H
+  double* d_out = nullptr;      // means / epilogue scratch
+  double* d_snap = nullptr;
+  PathState* d_paths = nullptr;
+  uint32_t* d_pixels = nullptr;
+  int64_t pixel_capacity = 0;
+  Queues q{};
+  double* d_bg = nullptr;
+  unsigned long long* h_count = nullptr;  // pinned, written by advance_kernel
+  unsigned long long* d_count_mapped = nullptr;
+  uint64_t total_rays = 0;
+  int32_t batch_paths = 1 << 22;
+};
+
+void render_state_free(izpi_ctx* ctx) {
+  RenderState* r = ctx->render;
+  if (!r) return;
+  cudaFree(r->d_canvas); cudaFree(r->d_out); cudaFree(r->d_snap); cudaFree(r->d_paths); cudaFree(r->d_pixels);
+  cudaFree(r->q.cur); cudaFree(r->q.next); cudaFree(r->q.bins); cudaFree(r->q.counters); cudaFree(r->d_bg);
+  if (r->h_count) cudaFreeHost(r->h_count);
+  delete r;
+  ctx->render = nullptr;
+}
+
+namespace {
+
+#include "cie_tables.inc"
+
+int upload_cie() {
+  static thread_local bool done = false;
+  if (done) return IZPI_OK;
+  IZ_CUDA(cudaMemcpyToSymbol(c_cie, kCieTable, sizeof(kCieTable)));
+  done = true;
+  return IZPI_OK;
+}
+
+template <typename K, typename... Args>
+int launch(izpi_ctx* ctx, K kern, dim3 grid, dim3 block, size_t smem, Args... args) {
+  kern<<<grid, block, smem, ctx->stream>>>(args...);
+  IZ_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return IZPI_OK;
+}
+
+int render_batch(izpi_ctx* ctx, RenderState* r, int n_pixels, int s_begin, int s_count) {
+  cudaStream_t st = ctx->stream;
+  const int sm = ctx->sm_count;
+  IZ_CUDA(cudaMemsetAsync(r->q.counters, 0, 9 * sizeof(unsigned long long), st));
+  long long n = (long long)n_pixels * s_count;
+  int rc;
+  int gen_grid = (int)std::min<long long>((n + 255) / 256, (long long)sm * 8);
+  if ((rc = launch(ctx, raygen_kernel, dim3(gen_grid), dim3(256), 0, ctx->scene, r->rp, r->d_paths, r->d_pixels, n_pixels,
+                   s_begin, s_count, r->q)) != IZPI_OK) return rc;
+  size_t smem = (size_t)kStackDepth * kThreads * sizeof(int32_t);
+  static thread_local int ext_blocks = 0;
+  if (!ext_blocks) {
+    IZ_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_blocks, extend_kernel, kThreads, smem));
+    if (ext_blocks < 1) ext_blocks = 1;
+  }
+  unsigned long long live = (unsigned long long)n;  // upper bound for bounce 0
+  for (int bounce = 0; bounce <= r->rp.max_depth && live > 0; bounce++) {
+    long long want = ((long long)live + kThreads - 1) / kThreads;
+    int eg = (int)std::min<long long>(want, (long long)sm * ext_blocks);
+    if ((rc = launch(ctx, extend_kernel, dim3(eg), dim3(kThreads), smem, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
+    int sg = (int)std::min<long long>(want, (long long)sm * 8);
+    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_LAMBERT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_METAL>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_DIELECTRIC>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_DIFFUSE_LIGHT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_PBR>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
+    std::swap(r->q.cur, r->q.next);
+    Queues qs = r->q;  // after the swap: cur = survivors; advance moves the count
+    if ((rc = launch(ctx, advance_kernel, dim3(1), dim3(1), 0, qs, r->d_count_mapped)) != IZPI_OK) return rc;
+    IZ_CUDA(cudaStreamSynchronize(st));
+    live = *r->h_count;
+  }
+  if ((rc = launch(ctx, resolve_kernel, dim3((n_pixels + 127) / 128), dim3(128), 0, r->rp, r->d_paths, r->d_pixels, n_pixels,
+                   s_count, r->d_canvas)) != IZPI_OK) return rc;
+  unsigned long long traced = 0;
+  IZ_CUDA(cudaMemcpyAsync(&traced, r->q.counters + 8, sizeof(traced), cudaMemcpyDeviceToHost, st));
+  IZ_CUDA(cudaStreamSynchronize(st));
+  r->total_rays += traced;
+  return IZPI_OK;
+}
+
+int canvas_to_host(izpi_ctx* ctx, RenderState* r, double* host, bool epilogue) {
+  cudaStream_t st = ctx->stream;
+  long long n_px = (long long)r->rp.width * r->rp.height;
+  int rc;
+  if ((rc = launch(ctx, mean_kernel, dim3((unsigned)((n_px + 255) / 256)), dim3(256), 0, r->rp, r->d_canvas, r->d_out, n_px)) != IZPI_OK) return rc;
+  if (epilogue && r->rp.sampler == IZPI_SAMPLER_SPECTRAL) {  // renderer.go:216-219
+    IZ_CUDA(cudaMemcpyAsync(r->d_snap, r->d_out, (size_t)n_px * 32, cudaMemcpyDeviceToDevice, st));
+    dim3 b(32, 8), g((r->rp.width + 31) / 32, (r->rp.height + 7) / 8);
+    if ((rc = launch(ctx, firefly_kernel, g, b, 0, r->d_snap, r->d_out, r->rp.width, r->rp.height)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, xyz_to_acescg_kernel, dim3((unsigned)((n_px + 255) / 256)), dim3(256), 0, r->d_out, n_px,
+                     ctx->scene.camera.exposure)) != IZPI_OK) return rc;
+  }
+  IZ_CUDA(cudaMemcpyAsync(host, r->d_out, (size_t)n_px * 32, cudaMemcpyDeviceToHost, st));
+  IZ_CUDA(cudaStreamSynchronize(st));
+  return IZPI_OK;
+}
+
+}  // namespace
 
 extern "C" {
-int izpi_render_setup(izpi_ctx*, const izpi_render_config*) { set_error("render: not implemented"); return IZPI_ESTATE; }
-int izpi_render_tiles(izpi_ctx*, int32_t, const uint32_t*, double*) { set_error("render: not implemented"); return IZPI_ESTATE; }
-int izpi_render_canvas_device(izpi_ctx*, double**) { set_error("render: not implemented"); return IZPI_ESTATE; }
-int izpi_render_finish(izpi_ctx*, double*, uint64_t*) { set_error("render: not implemented"); return IZPI_ESTATE; }
+
+int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
+  if (!ctx || !cfg) { set_error("izpi_render_setup: bad argument"); return IZPI_EINVAL; }
+  if (!ctx->has_scene) { set_error("izpi_render_setup: no scene uploaded"); return IZPI_ESTATE; }
+  if (cfg->width <= 0 || cfg->height <= 0 || cfg->width > 65535 || cfg->height > 65535 || cfg->spp <= 0 || cfg->max_depth < 0 ||
+      cfg->sample_count < 0 || cfg->sample_offset < 0 || cfg->sample_offset + cfg->sample_count > cfg->spp ||
+      (cfg->sampler != IZPI_SAMPLER_COLOUR && cfg->sampler != IZPI_SAMPLER_SPECTRAL)) {
+    set_error("izpi_render_setup: invalid configuration");
+    return IZPI_EINVAL;
+  }
+  if (ctx->scene.n_lights == 0) {  // HitableSlice.Random indexes an empty slice: the reference panics
+    set_error("izpi_render_setup: scene has no emitters (scene.Lights is empty)");
+    return IZPI_EINVAL;
+  }
+  if (!ctx->scene.attrs) { set_error("izpi_render_setup: scene was uploaded without tri_attrs"); return IZPI_ESTATE; }
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  int rc = upload_cie();
+  if (rc != IZPI_OK) return rc;
+  render_state_free(ctx);
+  auto* r = new RenderState();
+  ctx->render = r;
+  r->cfg = *cfg;
+  RenderParams& rp = r->rp;
+  rp.width = cfg->width; rp.height = cfg->height; rp.spp = cfg->spp; rp.max_depth = cfg->max_depth; rp.sampler = cfg->sampler;
+  for (int k = 0; k < 3; k++) rp.background[k] = cfg->background[k];
+  rp.seed = cfg->seed; rp.n_bg = 0; rp.bg_w = rp.bg_v = nullptr;
+  if (cfg->n_bg > 0 && cfg->bg_wavelengths && cfg->bg_values) {
+    IZ_CUDA(cudaMalloc(&r->d_bg, (size_t)cfg->n_bg * 16));
+    IZ_CUDA(cudaMemcpy(r->d_bg, cfg->bg_wavelengths, (size_t)cfg->n_bg * 8, cudaMemcpyHostToDevice));
+    IZ_CUDA(cudaMemcpy(r->d_bg + cfg->n_bg, cfg->bg_values, (size_t)cfg->n_bg * 8, cudaMemcpyHostToDevice));
+    rp.n_bg = cfg->n_bg; rp.bg_w = r->d_bg; rp.bg_v = r->d_bg + cfg->n_bg;
+  }
+  size_t n_px = (size_t)cfg->width * cfg->height;
+  IZ_CUDA(cudaMalloc(&r->d_canvas, n_px * 32));
+  IZ_CUDA(cudaMalloc(&r->d_out, n_px * 32));
+  IZ_CUDA(cudaMalloc(&r->d_snap, n_px * 32));
+  IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px * 32, ctx->stream));
+  int32_t cap = r->batch_paths;
+  IZ_CUDA(cudaMalloc(&r->d_paths, (size_t)cap * sizeof(PathState)));
+  IZ_CUDA(cudaMalloc(&r->q.cur, (size_t)cap * 4));
+  IZ_CUDA(cudaMalloc(&r->q.next, (size_t)cap * 4));
+  IZ_CUDA(cudaMalloc(&r->q.bins, (size_t)cap * 4 * kClasses));
+  IZ_CUDA(cudaMalloc(&r->q.counters, 16 * sizeof(unsigned long long)));
+  r->q.capacity = cap;
+  IZ_CUDA(cudaHostAlloc(&r->h_count, sizeof(unsigned long long), cudaHostAllocMapped));
+  IZ_CUDA(cudaHostGetDevicePointer(&r->d_count_mapped, r->h_count, 0));
+  IZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return IZPI_OK;
 }
+
+int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* tiles, double* canvas_rgba) {
+  if (!ctx || n_tiles < 0 || (n_tiles > 0 && !tiles)) { set_error("izpi_render_tiles: bad argument"); return IZPI_EINVAL; }
+  RenderState* r = ctx->render;
+  if (!r) { set_error("izpi_render_tiles: izpi_render_setup has not been called"); return IZPI_ESTATE; }
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  // pixel list in the reference's loop order: tiles as given, rows y0..y1, columns x0..x1 (rgb.go:27-29)
+  std::vector<uint32_t> px;
+  for (int32_t t = 0; t < n_tiles; t++) {
+    uint32_t x0 = tiles[4 * t], y0 = tiles[4 * t + 1], x1 = tiles[4 * t + 2], y1 = tiles[4 * t + 3];
+    if (x1 < x0 || y1 < y0 || x1 >= (uint32_t)r->rp.width || y1 >= (uint32_t)r->rp.height) {
+      set_error("izpi_render_tiles: tile outside the image");
+      return IZPI_EINVAL;
+    }
+    for (uint32_t y = y0; y <= y1; y++)
+      for (uint32_t x = x0; x <= x1; x++) px.push_back(x | (y << 16));
+  }
+  if ((int64_t)px.size() > r->pixel_capacity) {
+    cudaFree(r->d_pixels);
+    r->d_pixels = nullptr; r->pixel_capacity = 0;
+    IZ_CUDA(cudaMalloc(&r->d_pixels, px.size() * 4));
+    r->pixel_capacity = (int64_t)px.size();
+  }
+  const int s_total = r->cfg.sample_count, s_off = r->cfg.sample_offset;
+  if (!px.empty() && s_total > 0) {
+    // batches: as many samples per pixel as fit, then as many pixels as fit; sample blocks in
+    // increasing order so that every pixel's running sum adds its samples in the reference's order
+    const int64_t cap = r->q.capacity;
+    int s_block = (int)std::min<int64_t>(s_total, cap);
+    int64_t px_block = std::max<int64_t>(1, cap / s_block);
+    for (int64_t p0 = 0; p0 < (int64_t)px.size(); p0 += px_block) {
+      int np = (int)std::min<int64_t>(px_block, (int64_t)px.size() - p0);
+      IZ_CUDA(cudaMemcpyAsync(r->d_pixels, px.data() + p0, (size_t)np * 4, cudaMemcpyHostToDevice, ctx->stream));
+      for (int s0 = 0; s0 < s_total; s0 += s_block) {
+        int sc = std::min(s_block, s_total - s0);
+        int rc = render_batch(ctx, r, np, s_off + s0, sc);
+        if (rc != IZPI_OK) return rc;
+      }
+    }
+  }
+  if (canvas_rgba) return canvas_to_host(ctx, r, canvas_rgba, false);
+  return IZPI_OK;
+}
+
+int izpi_render_canvas_device(izpi_ctx* ctx, double** d_canvas) {
+  if (!ctx || !d_canvas) { set_error("izpi_render_canvas_device: bad argument"); return IZPI_EINVAL; }
+  if (!ctx->render) { set_error("izpi_render_canvas_device: izpi_render_setup has not been called"); return IZPI_ESTATE; }
+  IZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *d_canvas = ctx->render->d_canvas;
+  return IZPI_OK;
+}
+
+int izpi_render_finish(izpi_ctx* ctx, double* canvas_rgba, uint64_t* total_rays) {
+  if (!ctx) { set_error("izpi_render_finish: bad argument"); return IZPI_EINVAL; }
+  RenderState* r = ctx->render;
+  if (!r) { set_error("izpi_render_finish: izpi_render_setup has not been called"); return IZPI_ESTATE; }
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  if (total_rays) *total_rays = r->total_rays;
+  if (canvas_rgba) return canvas_to_host(ctx, r, canvas_rgba, true);
+  return IZPI_OK;
+}
+
+}  // extern "C"

@@ -176,14 +176,11 @@ __device__ __forceinline__ d3 light_random(const DScene& sc, int rec, d3 o, Rng&
       return onb_local(uvw, random_to_sphere(pr.a[3], dist2, rng));
     }
     case IZPI_PRIM_TRIANGLE: {
+      // Triangle.Random lerps between the ORIGINAL vertices (v0 + e1 would differ from vertex1 by a
+      // rounding), so the attribute record keeps vertex1 / vertex2.
       d3 v0 = mk(pr.a[0], pr.a[1], pr.a[2]);
-      // the record stores edges; vertex1/2 are recovered as the constructor's inputs only up to
-      // rounding, so the light table keeps them exactly: attrs are not needed, v1 = v0 + e1 is NOT
-      // used -- see light_vertices().
-      d3 v1 = mk(sc.attrs[rec].uv[0], 0, 0);  // placeholder, replaced below
-      (void)v1;
-      const double* lv = sc.light_verts + 6 * (size_t)sc.light_slot[rec];
-      d3 p1 = mk(lv[0], lv[1], lv[2]), p2 = mk(lv[3], lv[4], lv[5]);
+      const izpi_tri_attr& at = sc.attrs[rec];
+      d3 p1 = mk(at.vertex1[0], at.vertex1[1], at.vertex1[2]), p2 = mk(at.vertex2[0], at.vertex2[1], at.vertex2[2]);
       double t1 = rnd(rng);
       d3 p01 = lerp(v0, p1, t1);
       double t2 = rnd(rng);

@@ -66,6 +66,7 @@ void make_triangle(const double* p, izpi_prim_rec& rec, izpi_tri_attr& at, BoxD&
   wr3(at.normal, normal); wr3(at.tangent, tangent); wr3(at.bitangent, bitangent);
   at.uv[0] = u0; at.uv[1] = w0; at.uv[2] = u1; at.uv[3] = w1; at.uv[4] = u2; at.uv[5] = w2;
   at.area = len(n) / 2.0;
+  wr3(at.vertex1, v1); wr3(at.vertex2, v2);
   // vec3.Min3 / Max3, epsilon relative to the largest extent (triangle.go:100-113)
   double mn[3], mx[3];
   for (int k = 0; k < 3; k++) {
