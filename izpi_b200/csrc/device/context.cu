@@ -1,4 +1,5 @@
 // context.cu -- izpi_ctx lifetime and the one-time scene upload (include/izpi_cuda.h).
+#include <cstdlib>
 #include <cstring>
 
 #include "dscene.cuh"
@@ -47,6 +48,7 @@ int izpi_ctx_create(int n_devices, const int* device_ids, izpi_ctx** out) {
   IZ_CUDA(cudaSetDevice(dev));
   auto* ctx = new izpi_ctx();
   ctx->device = dev;
+  { const char* e = getenv("IZPI_FORCE_SCALAR"); ctx->force_scalar = e && e[0] == '1'; }
   cudaDeviceProp prop;
   IZ_CUDA(cudaGetDeviceProperties(&prop, dev));
   ctx->sm_count = prop.multiProcessorCount;
@@ -94,6 +96,55 @@ int izpi_scene_upload(izpi_ctx* ctx, const izpi_scene_desc* d) {
   const izpi_bvh4_node* dn = nullptr;
   if ((rc = upload(ctx, d->nodes, (size_t)d->n_nodes, &dn)) != IZPI_OK) return rc;
   s.nodes = reinterpret_cast<const float4*>(dn);
+  {
+    // Child-major node copy for the 4-lanes-per-ray traversal (intersect_g4.cuh).  A child that is one of
+    // the reference's leaf-nodes (own node, slot 0 only, bvh4.go:737-760) whose box equals the parent's
+    // slot box bit for bit (bvh4.go:750-755 vs :782-787) is folded into the parent slot as
+    // (first primitive, count).  Trees of any other shape keep the scalar traversal.
+    struct Child { float mnx, mny, mnz, mxx, mxy, mxz; int32_t idx, cnt; };
+    static_assert(sizeof(Child) == 32, "child record");
+    const int nn = d->n_nodes;
+    std::vector<Child> t((size_t)nn * 4);
+    auto pure_leaf = [&](const izpi_bvh4_node& n) {
+      return n.primitive_count[0] > 0 && n.child_index[0] >= 0 && n.child_index[1] == -1 && n.child_index[2] == -1 && n.child_index[3] == -1;
+    };
+    bool ok = nn > 0 && d->n_prims < (1 << 29);
+    for (int i = 0; i < nn && ok; i++) {
+      const izpi_bvh4_node& n = d->nodes[i];
+      const bool self_leaf = pure_leaf(n);
+      for (int k = 0; k < 4; k++) {
+        Child& c = t[(size_t)i * 4 + k];
+        c.mnx = n.min_x[k]; c.mny = n.min_y[k]; c.mnz = n.min_z[k]; c.mxx = n.max_x[k]; c.mxy = n.max_y[k]; c.mxz = n.max_z[k];
+        c.idx = n.child_index[k]; c.cnt = 0;
+        if (n.child_index[k] == -1) continue;
+        if (n.primitive_count[k] > 0) {
+          // a direct leaf slot is only representable when its node is a pure leaf-node reached as the root
+          if (!self_leaf) ok = false;
+          if (n.primitive_count[k] > 4 || n.child_index[k] + n.primitive_count[k] > d->n_prims) ok = false;
+          c.cnt = n.primitive_count[k];
+          continue;
+        }
+        if (n.child_index[k] < 0 || n.child_index[k] >= nn) { ok = false; break; }
+        const izpi_bvh4_node& ch = d->nodes[n.child_index[k]];
+        if (pure_leaf(ch)) {
+          bool same = ch.min_x[0] == n.min_x[k] && ch.min_y[0] == n.min_y[k] && ch.min_z[0] == n.min_z[k] &&
+                      ch.max_x[0] == n.max_x[k] && ch.max_y[0] == n.max_y[k] && ch.max_z[0] == n.max_z[k];
+          if (!same || ch.primitive_count[0] > 4 || ch.child_index[0] + ch.primitive_count[0] > d->n_prims) { ok = false; break; }
+          c.idx = ch.child_index[0]; c.cnt = ch.primitive_count[0];
+        } else {
+          for (int q = 0; q < 4; q++) if (ch.child_index[q] != -1 && ch.primitive_count[q] > 0) ok = false;  // mixed node
+        }
+      }
+    }
+    s.g4_ok = ok ? 1 : 0;
+    s.root_is_leaf = (ok && pure_leaf(d->nodes[0])) ? 1 : 0;
+    if (ok) {
+      const Child* dt = nullptr;
+      if ((rc = upload(ctx, t.data(), t.size(), &dt)) != IZPI_OK) return rc;
+      IZ_CUDA(cudaStreamSynchronize(ctx->stream));  // `t` is a local
+      s.nodes_t = reinterpret_cast<const float4*>(dt);
+    }
+  }
   if ((rc = upload(ctx, d->prims, (size_t)d->n_prims, &s.prims)) != IZPI_OK) return rc;
   if (d->tri_attrs && (rc = upload(ctx, d->tri_attrs, (size_t)d->n_prims, &s.attrs)) != IZPI_OK) return rc;
   if ((rc = upload(ctx, d->xforms, (size_t)d->n_xforms, &s.xforms)) != IZPI_OK) return rc;

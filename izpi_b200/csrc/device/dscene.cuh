@@ -27,8 +27,11 @@ struct DSpectralTexture {  // texture.SpectralConstant
 };
 
 struct DScene {
-  int32_t world_kind, n_nodes, n_prims, n_xforms, n_lights, n_materials, dielectric_has_world, pad;
-  const float4* nodes;          // 8 x float4 per BVH4Node, 128-B aligned
+  int32_t world_kind, n_nodes, n_prims, n_xforms, n_lights, n_materials, dielectric_has_world;
+  int32_t g4_ok;                // nodes_t is usable (reference-shaped tree: leaves are own slot-0-only nodes)
+  int32_t root_is_leaf, pad;
+  const float4* nodes;          // 8 x float4 per BVH4Node, verbatim SoA layout, 128-B aligned
+  const float4* nodes_t;        // child-major copy: 4 x {minx miny minz maxx | maxy maxz idx cnt}, leaf-nodes folded in
   const izpi_prim_rec* prims;   // 80-B records in world order, 16-B aligned
   const izpi_tri_attr* attrs;   // 128-B records, same index
   const izpi_xform* xforms;
@@ -57,6 +60,7 @@ struct izpi_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool has_scene = false;
+  bool force_scalar = false;  // IZPI_FORCE_SCALAR=1: thread-per-ray traversal even for reference-shaped trees
   izpi::DScene scene{};
   std::vector<void*> scene_allocs;  // freed on re-upload / destroy
   // trace scratch (grown on demand)

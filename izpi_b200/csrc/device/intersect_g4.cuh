@@ -97,7 +97,7 @@ __device__ __forceinline__ void g4_node(G4State& s, const DScene& sc, int2* stac
   if (nref >= 0) {
     s.cur = nref;  // first hit child is visited next (bvh4.go:137-140)
   } else {         // ... and when it is a leaf its box test repeats with the same tMax: it passes
-    if (COUNT) n_nodes++;
+    if (COUNT && !sc.root_is_leaf) n_nodes++;  // (a root that is itself the leaf-node was already counted)
     int v = ~nref;
     s.cur = kLeaf; s.leaf_start = v >> 2; s.leaf_cnt = (v & 3) + 1;
   }

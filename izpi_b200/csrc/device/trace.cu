@@ -3,7 +3,7 @@
 // the BVH4 in the reference's order with its own short stack in shared memory.
 #include <cstring>
 
-#include "intersect.cuh"
+#include "intersect_g4.cuh"
 
 using namespace izpi;
 
@@ -45,6 +45,78 @@ trace_kernel(const __grid_constant__ DScene sc, long long n, const double* __res
   }
 }
 
+// ---- 4 lanes per ray -------------------------------------------------------------------------
+// Each warp owns 8 ray slots.  Rays are drawn from the global queue in chunks of kChunk per warp (one
+// atomicAdd per chunk), handed to idle groups as they finish (persistent threads with ray replacement),
+// and the warp alternates between a node phase and a leaf phase (intersect_g4.cuh).
+constexpr int kChunk = 256;
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads)
+trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __restrict__ org,
+                const double* __restrict__ dir, double tmin, double tmax, int32_t* __restrict__ ids,
+                double* __restrict__ ts, unsigned long long* counters) {
+  extern __shared__ int2 g4_stack_smem[];  // [rays per block][kG4Stack + 1]: one private stack per ray
+  const unsigned lane = threadIdx.x & 31u;
+  const int g = lane >> 2, j = lane & 3;
+  const int gshift = g * 4;
+  const unsigned gmask = 0xfu << gshift;
+  int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 2) * (kG4Stack + 1);
+  uint32_t n_nodes = 0, n_prims = 0;
+  long long chunk_next = 0, chunk_end = 0;  // warp-uniform
+  bool exhausted = false;
+  G4State s;
+  s.cur = kIdle;
+  long long ray = -1;
+  for (;;) {
+    // ---- hand rays to idle groups
+    unsigned idle = __ballot_sync(0xffffffffu, s.cur == kIdle);
+    if (idle) {
+      if (chunk_next >= chunk_end && !exhausted) {
+        long long b = 0;
+        if (lane == 0) b = (long long)atomicAdd(&counters[0], (unsigned long long)kChunk);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        chunk_next = b;
+        chunk_end = b + kChunk < n ? b + kChunk : n;
+        if (b >= n) { exhausted = true; chunk_next = chunk_end = 0; }
+      }
+      int before = __popc(idle & ((1u << gshift) - 1u)) >> 2;  // idle groups ahead of mine
+      int total = __popc(idle) >> 2;
+      if (s.cur == kIdle && chunk_next + before < chunk_end) {
+        ray = chunk_next + before;
+        DRay r;
+        r.o = mk(org[3 * ray], org[3 * ray + 1], org[3 * ray + 2]);
+        r.d = mk(dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2]);
+        r.time = 0; r.lambda = 0;
+        g4_begin(s, sc, r, tmin, tmax);
+        if (s.cur == kIdle && j == 0) { ids[ray] = -1; ts[ray] = 0.0; }
+      }
+      long long take = chunk_end - chunk_next;
+      chunk_next += take < total ? take : total;
+      if (exhausted && __ballot_sync(0xffffffffu, s.cur == kIdle) == 0xffffffffu) break;
+    }
+    // ---- node phase: every group that stands on an inner node visits it
+    while (s.cur >= 0) g4_node<COUNT>(s, sc, stack, gmask, gshift, j, n_nodes);
+    __syncwarp();
+    // ---- leaf phase
+    if (s.cur == kLeaf) g4_leaf<COUNT>(s, sc, stack, gmask, gshift, j, n_nodes, n_prims);
+    __syncwarp();
+    // ---- finished rays write their answer
+    if (s.cur == kIdle && ray >= 0) {
+      if (j == 0) {
+        ids[ray] = s.best >= 0 ? sc.prims[s.best].orig_id : -1;
+        ts[ray] = s.best >= 0 ? s.tmax : 0.0;
+      }
+      ray = -1;
+    }
+  }
+  if (COUNT && j == 0) {
+    atomicAdd(&counters[1], (unsigned long long)n_nodes);
+    atomicAdd(&counters[2], (unsigned long long)n_prims);
+  }
+  if (COUNT && j != 0) atomicAdd(&counters[2], (unsigned long long)n_prims);
+}
+
 // Diagnostic: the 4-wide slab test alone, so the reference's golden masks can be replayed on the device.
 __global__ void box4_kernel(int n, const float* __restrict__ org, const float* __restrict__ inv,
                             const float* __restrict__ bounds, const float* __restrict__ tmax, uint8_t* __restrict__ masks) {
@@ -61,6 +133,23 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
                  int mode, int32_t* d_ids, double* d_t, cudaStream_t st, bool count) {
   if (mode != IZPI_TRACE_EXACT) { set_error("izpi_trace_closest: only IZPI_TRACE_EXACT is implemented"); return IZPI_EINVAL; }
   IZ_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(unsigned long long), st));
+  if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar) {
+    size_t smem4 = (size_t)(kTraceThreads / 4) * (kG4Stack + 1) * sizeof(int2);
+    auto k4 = count ? trace_g4_kernel<true> : trace_g4_kernel<false>;
+    static thread_local int bps4 = 0;
+    if (!bps4) {
+      IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps4, trace_g4_kernel<false>, kTraceThreads, smem4));
+      if (bps4 < 1) bps4 = 1;
+    }
+    long long want4 = (n + (kTraceThreads / 4) - 1) / (kTraceThreads / 4);
+    long long grid4 = (long long)ctx->sm_count * bps4;
+    if (grid4 > want4) grid4 = want4;
+    if (grid4 < 1) grid4 = 1;
+    k4<<<(unsigned)grid4, kTraceThreads, smem4, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, ctx->d_counters);
+    IZ_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return IZPI_OK;
+  }
   size_t smem = (size_t)kStackDepth * kTraceThreads * sizeof(int32_t);
   auto kern = count ? trace_kernel<true> : trace_kernel<false>;
   static thread_local int blocks_per_sm = 0;
