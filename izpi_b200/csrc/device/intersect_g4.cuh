@@ -3,7 +3,8 @@
 // Same results as (*BVH4).Hit (internal/hitable/bvh4.go:49-164) in the same order, organised for
 // the SIMT machine instead of one scalar loop per ray:
 //   * lane j of a ray group owns child slot j of the node being visited: one 32-byte child record
-//     (two 128-bit loads), one fp32 slab test, then a 4-bit group ballot decides next / pushes;
+//     (two 128-bit loads), one fp32 slab test, then a warp ballot (4 bits per group) decides
+//     next / pushes;
 //   * the reference's leaf-nodes (own node, slot 0 only, bvh4.go:737-760) are folded into their
 //     parent's slot at upload time: the slot carries (first primitive, count) and the entry pushed on
 //     the stack keeps the slab-entry distance, so "visiting the leaf node" becomes the single
@@ -14,124 +15,151 @@
 //     entry and then resolved in array order with the shrinking-tMax rule (a primitive accepted
 //     sequentially is exactly one accepted against the entry tMax whose t also passes the running
 //     tMax);
-//   * node phase and leaf phase alternate warp-wide (while-while traversal), so the 8 groups of a warp
-//     execute box tests together and primitive tests together.
+//   * node phase and leaf phase alternate warp-wide.  Both are warp-uniform loops with predicated
+//     bodies, so every collective uses the full mask (sub-warp masks make the compiler serialise one
+//     group at a time).  The node phase ends as soon as at most kNodeStragglers groups still stand on
+//     an inner node while leaves are pending (profiles/sim_schedule.py: waiting for the last group
+//     costs 1.4x more warp instructions).
 #pragma once
 #include "intersect.cuh"
 
 namespace izpi {
 
-constexpr int kG4Stack = 64;  // entries per ray (bvh4.go:71)
+constexpr int kG4Stack = 64;        // entries per ray (bvh4.go:71)
+constexpr int kNodeStragglers = 3;  // leave the node phase when <= this many groups are still in it
 
 struct G4State {
   DRay r;
   float ox, oy, oz, ix, iy, iz;
   double tmin, tmax;
-  int best;        // record index of the closest primitive so far
-  int sp;          // stack pointer
-  int cur;         // >= 0: inner node to visit; kLeaf: leaf pending; kIdle: no ray
-  int leaf_start, leaf_cnt;
+  int best;   // record index of the closest primitive so far
+  int sp;     // stack pointer
+  int cur;    // >= 0: inner node to visit; kLeaf: leaf pending; kIdle: no ray
+  int leaf;   // pending leaf: (first primitive << 2) | (count - 1)
+  bool fast;  // no NaN can arise in the slab test: FMNMX min/max equal the SSE selects
 };
 constexpr int kLeaf = -2, kIdle = -1;
 
 // stack entry: ref >= 0 inner node; ref < 0 leaf: ~ref = (first primitive << 2) | (count - 1)
-__device__ __forceinline__ int leaf_ref(int start, int cnt) { return ~((start << 2) | (cnt - 1)); }
-
 __device__ __forceinline__ void g4_begin(G4State& s, const DScene& sc, const DRay& r, double tmin, double tmax) {
   s.r = r;
   s.ix = (float)(1.0 / r.d.x); s.iy = (float)(1.0 / r.d.y); s.iz = (float)(1.0 / r.d.z);  // bvh4.go:61-66
   s.ox = (float)r.o.x; s.oy = (float)r.o.y; s.oz = (float)r.o.z;                            // bvh4.go:67
   s.tmin = tmin; s.tmax = tmax; s.best = -1; s.sp = 0;
   s.cur = sc.n_nodes > 0 ? 0 : kIdle;
-  s.leaf_start = 0; s.leaf_cnt = 0;
+  s.leaf = 0;
+  // (bound - o) * inv is NaN only for 0 * Inf or Inf * 0: impossible when the origin is small enough for the
+  // subtraction not to overflow and 1/d is finite and non-zero.  MINPS/MAXPS then agree with FMNMX (up to the
+  // sign of zero, which no comparison below sees).
+  const float big = 1e30f;
+  s.fast = fabsf(s.ox) < big && fabsf(s.oy) < big && fabsf(s.oz) < big && fabsf(s.ix) <= 3.0e38f && fabsf(s.iy) <= 3.0e38f &&
+           fabsf(s.iz) <= 3.0e38f && s.ix != 0.0f && s.iy != 0.0f && s.iz != 0.0f;
 }
 
-// Pop until something to do is found.  Returns false when the stack is empty (ray finished).
+// Pop until something to do is found; leaves the ray idle when the stack is empty.
 template <bool COUNT>
-__device__ __forceinline__ bool g4_pop(G4State& s, const int2* stack, uint32_t& n_nodes) {
+__device__ __forceinline__ void g4_pop(G4State& s, const int2* stack, uint32_t& n_nodes) {
   while (s.sp > 0) {
     s.sp--;
     int2 e = stack[s.sp];
-    if (e.x >= 0) { s.cur = e.x; return true; }
+    if (e.x >= 0) { s.cur = e.x; return; }
     if (COUNT) n_nodes++;  // the reference loads the leaf node before its box test can fail
-    if ((float)s.tmax >= __int_as_float(e.y)) {
-      int v = ~e.x;
-      s.cur = kLeaf; s.leaf_start = v >> 2; s.leaf_cnt = (v & 3) + 1;
-      return true;
-    }
+    if ((float)s.tmax >= __int_as_float(e.y)) { s.cur = kLeaf; s.leaf = ~e.x; return; }
   }
-  return false;
+  s.cur = kIdle;
 }
 
-// One inner-node visit by the 4 lanes of a group.  gmask = this group's lanes, j = lane within group.
+// Node phase for the whole warp.  gshift = 4 * group, j = lane within group.
 template <bool COUNT>
-__device__ __forceinline__ void g4_node(G4State& s, const DScene& sc, int2* stack, unsigned gmask, int gshift, int j,
-                                        uint32_t& n_nodes) {
-  const float4* np = sc.nodes_t + (size_t)s.cur * 8 + 2 * j;
-  const float4 a = __ldg(np);
-  const float4 b = __ldg(np + 1);
-  const int idx = __float_as_int(b.z), cnt = __float_as_int(b.w);
-  if (COUNT) n_nodes++;
-  const float tmaxf = (float)s.tmax;  // float32(tMax) at node entry (bvh4.go:100)
-  // one lane of RayAABB4_SIMD (bvh4_simd_amd64.go:52-101); tnear is its t_min
-  float t0 = __fmul_rn(__fsub_rn(a.x, s.ox), s.ix), t1 = __fmul_rn(__fsub_rn(a.w, s.ox), s.ix);
-  float tmn = sse_min(t0, t1), tmx = sse_max(t0, t1);
-  t0 = __fmul_rn(__fsub_rn(a.y, s.oy), s.iy); t1 = __fmul_rn(__fsub_rn(b.x, s.oy), s.iy);
-  tmn = sse_max(tmn, sse_min(t0, t1)); tmx = sse_min(tmx, sse_max(t0, t1));
-  t0 = __fmul_rn(__fsub_rn(a.z, s.oz), s.iz); t1 = __fmul_rn(__fsub_rn(b.y, s.oz), s.iz);
-  tmn = sse_max(tmn, sse_min(t0, t1)); tmx = sse_min(tmx, sse_max(t0, t1));
-  const bool hit = (tmx >= tmn) && (tmx >= 0.0f) && (tmaxf >= tmn) && (idx != -1);
-  const unsigned m = (__ballot_sync(gmask, hit) >> gshift) & 0xfu;
-  if (m == 0) {
-    if (!g4_pop<COUNT>(s, stack, n_nodes)) s.cur = kIdle;
-    return;
+__device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2* stack, unsigned lane, int gshift, int j,
+                                              uint32_t& n_nodes) {
+  const unsigned full = 0xffffffffu;
+  for (;;) {
+    const bool in_node = s.cur >= 0;
+    const unsigned nm = __ballot_sync(full, in_node);
+    if (nm == 0) break;
+    if (__popc(nm) <= 4 * kNodeStragglers && __any_sync(full, s.cur == kLeaf)) break;
+    bool hit = false;
+    float tmn = 0.0f;
+    int ref = 0;
+    if (in_node) {
+      const float4* np = sc.nodes_t + (size_t)s.cur * 8 + 2 * j;
+      const float4 a = __ldg(np);
+      const float4 b = __ldg(np + 1);
+      const int idx = __float_as_int(b.z), cnt = __float_as_int(b.w);
+      if (COUNT) n_nodes++;
+      const float tmaxf = (float)s.tmax;  // float32(tMax) at node entry (bvh4.go:100)
+      // one lane of RayAABB4_SIMD (bvh4_simd_amd64.go:52-101); tmn is its t_min, tmx its t_max
+      const float t0x = __fmul_rn(__fsub_rn(a.x, s.ox), s.ix), t1x = __fmul_rn(__fsub_rn(a.w, s.ox), s.ix);
+      const float t0y = __fmul_rn(__fsub_rn(a.y, s.oy), s.iy), t1y = __fmul_rn(__fsub_rn(b.x, s.oy), s.iy);
+      const float t0z = __fmul_rn(__fsub_rn(a.z, s.oz), s.iz), t1z = __fmul_rn(__fsub_rn(b.y, s.oz), s.iz);
+      float tmx;
+      if (s.fast) {
+        tmn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+        tmx = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+      } else {
+        tmn = sse_min(t0x, t1x); tmx = sse_max(t0x, t1x);
+        tmn = sse_max(tmn, sse_min(t0y, t1y)); tmx = sse_min(tmx, sse_max(t0y, t1y));
+        tmn = sse_max(tmn, sse_min(t0z, t1z)); tmx = sse_min(tmx, sse_max(t0z, t1z));
+      }
+      hit = (tmx >= tmn) && (tmx >= 0.0f) && (tmaxf >= tmn) && (idx != -1);
+      ref = cnt > 0 ? ~((idx << 2) | (cnt - 1)) : idx;
+    }
+    const unsigned m = (__ballot_sync(full, hit) >> gshift) & 0xfu;
+    const int first = m ? __ffs(m) - 1 : 0;
+    const int nref = __shfl_sync(full, ref, (lane & ~3u) + first);
+    if (in_node) {
+      if (m == 0) {
+        g4_pop<COUNT>(s, stack, n_nodes);
+      } else {
+        if (hit && j != first)  // later hit children are pushed in slot order (bvh4.go:141-145)
+          stack[s.sp + __popc(m & ((1u << j) - 1u)) - 1] = make_int2(ref, __float_as_int(tmn));
+        s.sp += __popc(m) - 1;
+        if (nref >= 0) {
+          s.cur = nref;  // first hit child is visited next (bvh4.go:137-140)
+        } else {         // ... and when it is a leaf its box test repeats with the same tMax: it passes
+          if (COUNT && !sc.root_is_leaf) n_nodes++;  // (a root that is itself the leaf-node was already counted)
+          s.cur = kLeaf; s.leaf = ~nref;
+        }
+      }
+    }
+    __syncwarp();  // pushes visible to the group before any pop
   }
-  const int first = __ffs(m) - 1;
-  const int ref = cnt > 0 ? leaf_ref(idx, cnt) : idx;
-  if (hit && j != first) {  // later hit children are pushed in slot order (bvh4.go:141-145)
-    int rank = __popc(m & ((1u << j) - 1u)) - 1;
-    stack[s.sp + rank] = make_int2(ref, __float_as_int(tmn));
-  }
-  s.sp += __popc(m) - 1;
-  const int nref = __shfl_sync(gmask, ref, first, 4);
-  if (nref >= 0) {
-    s.cur = nref;  // first hit child is visited next (bvh4.go:137-140)
-  } else {         // ... and when it is a leaf its box test repeats with the same tMax: it passes
-    if (COUNT && !sc.root_is_leaf) n_nodes++;  // (a root that is itself the leaf-node was already counted)
-    int v = ~nref;
-    s.cur = kLeaf; s.leaf_start = v >> 2; s.leaf_cnt = (v & 3) + 1;
-  }
-  __syncwarp(gmask);  // pushes visible to the group before any pop
 }
 
-// Leaf visit: lane j tests primitive j; the group then replays the reference's sequential
+// Leaf phase: lane j tests primitive j; the group then replays the reference's sequential
 // `if hit { tMax = rec.T() }` loop (bvh4.go:125-134) over the four candidates.
 template <bool COUNT>
-__device__ __forceinline__ void g4_leaf(G4State& s, const DScene& sc, const int2* stack, unsigned gmask, int gshift, int j,
-                                        uint32_t& n_nodes, uint32_t& n_prims) {
+__device__ __forceinline__ void g4_leaf_phase(G4State& s, const DScene& sc, const int2* stack, unsigned lane, int gshift, int j,
+                                              uint32_t& n_nodes, uint32_t& n_prims) {
+  const unsigned full = 0xffffffffu;
+  const bool in_leaf = s.cur == kLeaf;
+  if (!__any_sync(full, in_leaf)) return;
+  const int start = s.leaf >> 2, cnt = (s.leaf & 3) + 1;
   bool ok = false, strict = false;
   double t = 0;
-  if (j < s.leaf_cnt) {
-    PrimRec pr = load_rec(sc.prims + s.leaf_start + j);
+  if (in_leaf && j < cnt) {
+    PrimRec pr = load_rec(sc.prims + start + j);
     DHit h;
-    ok = prim_hit<false>(sc, s.leaf_start + j, pr, s.r, s.tmin, s.tmax, h);
+    ok = prim_hit<false>(sc, start + j, pr, s.r, s.tmin, s.tmax, h);
     t = h.t;
     strict = tag_type(pr.tag) == IZPI_PRIM_SPHERE;  // Sphere.Hit compares strictly (sphere.go:73,84)
+    if (COUNT) n_prims++;
   }
-  if (COUNT) n_prims += (uint32_t)(j < s.leaf_cnt);
-  const unsigned okm = (__ballot_sync(gmask, ok) >> gshift) & 0xfu;
-  const unsigned stm = (__ballot_sync(gmask, strict) >> gshift) & 0xfu;
-  if (okm) {
+  const unsigned okw = __ballot_sync(full, ok);
+  if (okw) {  // a hit anywhere in the warp is rare (about one per ray): resolve only then
+    const unsigned stw = __ballot_sync(full, strict);
+    const unsigned okm = (okw >> gshift) & 0xfu, stm = (stw >> gshift) & 0xfu;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      double tk = __shfl_sync(gmask, t, k, 4);
+      double tk = __shfl_sync(full, t, (lane & ~3u) + k);
       if ((okm >> k) & 1u) {
         bool acc = ((stm >> k) & 1u) ? (tk < s.tmax) : (tk <= s.tmax);
-        if (acc) { s.tmax = tk; s.best = s.leaf_start + k; }
+        if (acc) { s.tmax = tk; s.best = start + k; }
       }
     }
   }
-  if (!g4_pop<COUNT>(s, stack, n_nodes)) s.cur = kIdle;
+  if (in_leaf) g4_pop<COUNT>(s, stack, n_nodes);
 }
 
 }  // namespace izpi

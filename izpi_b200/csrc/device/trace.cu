@@ -95,12 +95,9 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
       chunk_next += take < total ? take : total;
       if (exhausted && __ballot_sync(0xffffffffu, s.cur == kIdle) == 0xffffffffu) break;
     }
-    // ---- node phase: every group that stands on an inner node visits it
-    while (s.cur >= 0) g4_node<COUNT>(s, sc, stack, gmask, gshift, j, n_nodes);
-    __syncwarp();
-    // ---- leaf phase
-    if (s.cur == kLeaf) g4_leaf<COUNT>(s, sc, stack, gmask, gshift, j, n_nodes, n_prims);
-    __syncwarp();
+    // ---- node phase, then leaf phase (both warp-uniform)
+    g4_node_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes);
+    g4_leaf_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, n_prims);
     // ---- finished rays write their answer
     if (s.cur == kIdle && ray >= 0) {
       if (j == 0) {

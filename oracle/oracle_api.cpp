@@ -336,3 +336,39 @@ void oracle_xyz_to_rgb(const double* in, double* out, int32_t width, int32_t hei
 }
 
 }  // extern "C"
+
+// ---- design aid: per-ray step sequence of the exact traversal (N = inner node visit, L = leaf-node visit whose
+// box test passes and primitives are tested, F = leaf-node visit whose box test fails).  Used by
+// profiles/sim_schedule.py to evaluate SIMT scheduling policies offline; not part of any parity check.
+extern "C" int64_t oracle_trace_steps(const oracle_scene* s, int64_t n, const double* org, const double* dir, double tmin,
+                                      double tmax, char* out, int64_t out_cap, int64_t* offsets) {
+  const BVH4* bvh = s->bvh.get();
+  if (!bvh) return -1;
+  int64_t pos = 0;
+  for (int64_t i = 0; i < n; i++) {
+    offsets[i] = pos;
+    Ray r = NewRay(V(org[3 * i], org[3 * i + 1], org[3 * i + 2]), V(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), 0);
+    float inv[3] = {(float)(1.0 / r.direction.X), (float)(1.0 / r.direction.Y), (float)(1.0 / r.direction.Z)};
+    float o[3] = {(float)r.origin.X, (float)r.origin.Y, (float)r.origin.Z};
+    int32_t stack[64]; int sp = 0; int32_t cur = 0; double tM = tmax;
+    HitRecord rec; const Material* m;
+    while (cur != -1) {
+      const izpi_bvh4_node& node = bvh->Nodes[cur];
+      uint8_t mask = RayAABB4(BOX_SSE, o, inv, node, (float)tM);
+      bool leafnode = node.primitive_count[0] > 0;
+      if (pos < out_cap) out[pos++] = leafnode ? ((mask & 1) ? 'L' : 'F') : 'N';
+      int32_t next = -1;
+      for (int k = 0; k < 4; k++) {
+        if (!((mask >> k) & 1) || node.child_index[k] == -1) continue;
+        if (node.primitive_count[k] > 0) {
+          for (int p = 0; p < node.primitive_count[k]; p++)
+            if (bvh->Primitives[node.child_index[k] + p]->Hit(r, tmin, tM, rec, m)) tM = rec.t;
+        } else if (next == -1) next = node.child_index[k];
+        else stack[sp++] = node.child_index[k];
+      }
+      cur = next != -1 ? next : (sp > 0 ? stack[--sp] : -1);
+    }
+  }
+  offsets[n] = pos;
+  return pos;
+}
