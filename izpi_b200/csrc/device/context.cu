@@ -49,6 +49,7 @@ int izpi_ctx_create(int n_devices, const int* device_ids, izpi_ctx** out) {
   auto* ctx = new izpi_ctx();
   ctx->device = dev;
   { const char* e = getenv("IZPI_FORCE_SCALAR"); ctx->force_scalar = e && e[0] == '1'; }
+  { const char* e = getenv("IZPI_NODE_STRAGGLERS"); if (e && e[0] >= '0' && e[0] <= '7') ctx->node_stragglers = e[0] - '0'; }
   cudaDeviceProp prop;
   IZ_CUDA(cudaGetDeviceProperties(&prop, dev));
   ctx->sm_count = prop.multiProcessorCount;

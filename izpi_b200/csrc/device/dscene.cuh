@@ -60,6 +60,7 @@ struct izpi_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool has_scene = false;
+  int node_stragglers = 4;    // IZPI_NODE_STRAGGLERS: node-phase exit threshold of the 4-lanes-per-ray kernels
   bool force_scalar = false;  // IZPI_FORCE_SCALAR=1: thread-per-ray traversal even for reference-shaped trees
   izpi::DScene scene{};
   std::vector<void*> scene_allocs;  // freed on re-upload / destroy

@@ -26,7 +26,7 @@
 namespace izpi {
 
 constexpr int kG4Stack = 64;        // entries per ray (bvh4.go:71)
-constexpr int kNodeStragglers = 3;  // leave the node phase when <= this many groups are still in it
+constexpr int kNodeStragglers = 4;  // default: leave the node phase when <= this many groups are still in it
 
 struct G4State {
   DRay r;
@@ -72,13 +72,13 @@ __device__ __forceinline__ void g4_pop(G4State& s, const int2* stack, uint32_t& 
 // Node phase for the whole warp.  gshift = 4 * group, j = lane within group.
 template <bool COUNT>
 __device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2* stack, unsigned lane, int gshift, int j,
-                                              uint32_t& n_nodes) {
+                                              uint32_t& n_nodes, int stragglers = kNodeStragglers) {
   const unsigned full = 0xffffffffu;
   for (;;) {
     const bool in_node = s.cur >= 0;
     const unsigned nm = __ballot_sync(full, in_node);
     if (nm == 0) break;
-    if (__popc(nm) <= 4 * kNodeStragglers && __any_sync(full, s.cur == kLeaf)) break;
+    if (__popc(nm) <= 4 * stragglers && __any_sync(full, s.cur == kLeaf)) break;
     bool hit = false;
     float tmn = 0.0f;
     int ref = 0;

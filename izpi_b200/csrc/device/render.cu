@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include "intersect_g4.cuh"
 #include "shade.cuh"
 
 using namespace izpi;
@@ -199,6 +200,83 @@ extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* pat
     }
     __syncwarp();
     push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + 2);
+  }
+  if (traced) atomicAdd(&q.counters[8], traced);
+}
+
+// Same stage with the 4-lanes-per-ray traversal (intersect_g4.cuh) for reference-shaped BVH4 worlds:
+// 8 paths per warp, queue indices drawn in chunks, finished groups replaced immediately.
+constexpr int kExtendChunk = 256;
+
+__global__ void __launch_bounds__(kThreads)
+extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q, int stragglers) {
+  extern __shared__ int2 g4_stack_smem[];
+  const unsigned full = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const int j = lane & 3, gshift = (lane >> 2) * 4;
+  int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 2) * (kG4Stack + 1);
+  const long long n = (long long)q.counters[0];
+  // queue indices per atomicAdd: large when there is plenty of work, down to one packet of 8 when a late
+  // bounce has only a few thousand live paths (otherwise a handful of warps would walk them serially)
+  const long long warps = (long long)gridDim.x * (kThreads / 32);
+  long long chunk = (n / (warps * 4) + 7) & ~7ll;
+  chunk = chunk < 8 ? 8 : (chunk > kExtendChunk ? kExtendChunk : chunk);
+  uint32_t nn = 0, np = 0;
+  unsigned long long traced = 0;
+  long long chunk_next = 0, chunk_end = 0;
+  bool exhausted = false;
+  G4State s;
+  s.cur = kIdle;
+  int32_t pi = -1;
+  for (;;) {
+    unsigned idle = __ballot_sync(full, s.cur == kIdle);
+    if (idle) {
+      if (chunk_next >= chunk_end && !exhausted) {
+        long long b = 0;
+        if (lane == 0) b = (long long)atomicAdd(&q.counters[7], (unsigned long long)chunk);
+        b = __shfl_sync(full, b, 0);
+        chunk_next = b;
+        chunk_end = b + chunk < n ? b + chunk : n;
+        if (b >= n) { exhausted = true; chunk_next = chunk_end = 0; }
+      }
+      int before = __popc(idle & ((1u << gshift) - 1u)) >> 2, total = __popc(idle) >> 2;
+      if (s.cur == kIdle && chunk_next + before < chunk_end) {
+        pi = q.cur[chunk_next + before];
+        PathState& p = paths[pi];
+        if (p.depth >= rp.max_depth) {  // colour.go:34-36 / spectral.go:48-51
+          if (j == 0) {
+            d3 term = rp.sampler == IZPI_SAMPLER_COLOUR ? mk(0, 0, 1.0) : background_term(rp, p.lambda);
+            finish_path(rp, p, mk(p.ax, p.ay, p.az) + hadamard(mk(p.bx, p.by, p.bz), term));
+          }
+          pi = -1;
+        } else {
+          if (j == 0) traced++;  // atomic.AddUint64(numRays, 1) (colour.go:38)
+          g4_begin(s, sc, path_ray(p), 0.001, DBL_MAX);
+        }
+      }
+      long long take = chunk_end - chunk_next;
+      chunk_next += take < total ? take : total;
+      if (exhausted && __ballot_sync(full, s.cur == kIdle && pi < 0) == full) break;
+    }
+    g4_node_phase<false>(s, sc, stack, lane, gshift, j, nn, stragglers);
+    g4_leaf_phase<false>(s, sc, stack, lane, gshift, j, nn, np);
+    const bool done = s.cur == kIdle && pi >= 0;
+    if (__any_sync(full, done)) {
+      bool hit = false;
+      int cls = 0;
+      if (done && j == 0) {
+        PathState& p = paths[pi];
+        if (s.best < 0) {
+          finish_path(rp, p, mk(p.ax, p.ay, p.az) + hadamard(mk(p.bx, p.by, p.bz), background_term(rp, p.lambda)));
+        } else {
+          p.hit_rec = s.best; p.hit_t = s.tmax;
+          hit = true;
+          cls = sc.materials[tag_material(sc.prims[s.best].tag)].type;
+        }
+      }
+      push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + 2);
+      if (done) pi = -1;
+    }
   }
   if (traced) atomicAdd(&q.counters[8], traced);
 }
@@ -495,7 +573,9 @@ struct RenderState {
   unsigned long long* h_count = nullptr;  // pinned, written by advance_kernel
   unsigned long long* d_count_mapped = nullptr;
   uint64_t total_rays = 0;
-  int32_t batch_paths = 1 << 22;
+  int32_t batch_paths = 1 << 23;  // 8M paths x 160 B = 1.3 GB of HBM
+  size_t canvas_capacity = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
 void render_state_free(izpi_ctx* ctx) {
@@ -504,6 +584,8 @@ void render_state_free(izpi_ctx* ctx) {
   cudaFree(r->d_canvas); cudaFree(r->d_out); cudaFree(r->d_snap); cudaFree(r->d_paths); cudaFree(r->d_pixels);
   cudaFree(r->q.cur); cudaFree(r->q.next); cudaFree(r->q.bins); cudaFree(r->q.counters); cudaFree(r->d_bg);
   if (r->h_count) cudaFreeHost(r->h_count);
+  if (r->ev[0]) cudaEventDestroy(r->ev[0]);
+  if (r->ev[1]) cudaEventDestroy(r->ev[1]);
   delete r;
   ctx->render = nullptr;
 }
@@ -544,12 +626,30 @@ int render_batch(izpi_ctx* ctx, RenderState* r, int n_pixels, int s_begin, int s
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_blocks, extend_kernel, kThreads, smem));
     if (ext_blocks < 1) ext_blocks = 1;
   }
-  unsigned long long live = (unsigned long long)n;  // upper bound for bounce 0
-  for (int bounce = 0; bounce <= r->rp.max_depth && live > 0; bounce++) {
+  // tiny trees (config 4 has 22 primitives) stay cache-resident and coherent: the thread-per-ray stage wins there
+  const bool use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= 64;
+  const size_t smem4 = (size_t)(kThreads / 4) * (kG4Stack + 1) * sizeof(int2);
+  static thread_local int ext4_blocks = 0;
+  if (!ext4_blocks) {
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext4_blocks, extend_g4_kernel, kThreads, smem4));
+    if (ext4_blocks < 1) ext4_blocks = 1;
+  }
+  // The live-path count of bounce b is read back while bounce b+1 is already queued: the host never
+  // stalls the GPU between bounces.  Counts only shrink, so a stale count is a valid upper bound for
+  // grid sizing, and the loop stops one (empty) bounce after the queue ran dry.
+  unsigned long long live = (unsigned long long)n;
+  for (int bounce = 0; bounce <= r->rp.max_depth; bounce++) {
     long long want = ((long long)live + kThreads - 1) / kThreads;
-    int eg = (int)std::min<long long>(want, (long long)sm * ext_blocks);
-    if ((rc = launch(ctx, extend_kernel, dim3(eg), dim3(kThreads), smem, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
-    int sg = (int)std::min<long long>(want, (long long)sm * 8);
+    int eg = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * ext_blocks));
+    if (use_g4) {
+      long long want4 = ((long long)live + (kThreads / 4) - 1) / (kThreads / 4);
+      int eg4 = (int)std::max<long long>(1, std::min<long long>(want4, (long long)sm * ext4_blocks));
+      if ((rc = launch(ctx, extend_g4_kernel, dim3(eg4), dim3(kThreads), smem4, ctx->scene, r->rp, r->d_paths, r->q,
+                       ctx->node_stragglers)) != IZPI_OK) return rc;
+    } else if ((rc = launch(ctx, extend_kernel, dim3(eg), dim3(kThreads), smem, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) {
+      return rc;
+    }
+    int sg = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * 8));
     if ((rc = launch(ctx, shade_kernel<IZPI_MAT_LAMBERT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
     if ((rc = launch(ctx, shade_kernel<IZPI_MAT_METAL>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
     if ((rc = launch(ctx, shade_kernel<IZPI_MAT_DIELECTRIC>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
@@ -557,9 +657,13 @@ int render_batch(izpi_ctx* ctx, RenderState* r, int n_pixels, int s_begin, int s
     if ((rc = launch(ctx, shade_kernel<IZPI_MAT_PBR>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
     std::swap(r->q.cur, r->q.next);
     Queues qs = r->q;  // after the swap: cur = survivors; advance moves the count
-    if ((rc = launch(ctx, advance_kernel, dim3(1), dim3(1), 0, qs, r->d_count_mapped)) != IZPI_OK) return rc;
-    IZ_CUDA(cudaStreamSynchronize(st));
-    live = *r->h_count;
+    if ((rc = launch(ctx, advance_kernel, dim3(1), dim3(1), 0, qs, r->d_count_mapped + (bounce & 1))) != IZPI_OK) return rc;
+    IZ_CUDA(cudaEventRecord(r->ev[bounce & 1], st));
+    if (bounce >= 1) {
+      IZ_CUDA(cudaEventSynchronize(r->ev[(bounce - 1) & 1]));
+      live = r->h_count[(bounce - 1) & 1];
+      if (live == 0) break;
+    }
   }
   if ((rc = launch(ctx, resolve_kernel, dim3((n_pixels + 127) / 128), dim3(128), 0, r->rp, r->d_paths, r->d_pixels, n_pixels,
                    s_count, r->d_canvas)) != IZPI_OK) return rc;
@@ -608,34 +712,46 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
   IZ_CUDA(cudaSetDevice(ctx->device));
   int rc = upload_cie();
   if (rc != IZPI_OK) return rc;
-  render_state_free(ctx);
-  auto* r = new RenderState();
-  ctx->render = r;
+  // the big buffers (path states, queues, canvas) are allocated once per context and reused by later
+  // setups: a render call then costs no cudaMalloc / cudaFree
+  RenderState* r = ctx->render;
+  if (!r) { r = new RenderState(); ctx->render = r; }
   r->cfg = *cfg;
+  r->total_rays = 0;
   RenderParams& rp = r->rp;
   rp.width = cfg->width; rp.height = cfg->height; rp.spp = cfg->spp; rp.max_depth = cfg->max_depth; rp.sampler = cfg->sampler;
   for (int k = 0; k < 3; k++) rp.background[k] = cfg->background[k];
   rp.seed = cfg->seed; rp.n_bg = 0; rp.bg_w = rp.bg_v = nullptr;
   if (cfg->n_bg > 0 && cfg->bg_wavelengths && cfg->bg_values) {
+    cudaFree(r->d_bg); r->d_bg = nullptr;
     IZ_CUDA(cudaMalloc(&r->d_bg, (size_t)cfg->n_bg * 16));
     IZ_CUDA(cudaMemcpy(r->d_bg, cfg->bg_wavelengths, (size_t)cfg->n_bg * 8, cudaMemcpyHostToDevice));
     IZ_CUDA(cudaMemcpy(r->d_bg + cfg->n_bg, cfg->bg_values, (size_t)cfg->n_bg * 8, cudaMemcpyHostToDevice));
     rp.n_bg = cfg->n_bg; rp.bg_w = r->d_bg; rp.bg_v = r->d_bg + cfg->n_bg;
   }
   size_t n_px = (size_t)cfg->width * cfg->height;
-  IZ_CUDA(cudaMalloc(&r->d_canvas, n_px * 32));
-  IZ_CUDA(cudaMalloc(&r->d_out, n_px * 32));
-  IZ_CUDA(cudaMalloc(&r->d_snap, n_px * 32));
+  if (n_px > r->canvas_capacity) {
+    cudaFree(r->d_canvas); cudaFree(r->d_out); cudaFree(r->d_snap);
+    r->d_canvas = r->d_out = r->d_snap = nullptr; r->canvas_capacity = 0;
+    IZ_CUDA(cudaMalloc(&r->d_canvas, n_px * 32));
+    IZ_CUDA(cudaMalloc(&r->d_out, n_px * 32));
+    IZ_CUDA(cudaMalloc(&r->d_snap, n_px * 32));
+    r->canvas_capacity = n_px;
+  }
   IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px * 32, ctx->stream));
-  int32_t cap = r->batch_paths;
-  IZ_CUDA(cudaMalloc(&r->d_paths, (size_t)cap * sizeof(PathState)));
-  IZ_CUDA(cudaMalloc(&r->q.cur, (size_t)cap * 4));
-  IZ_CUDA(cudaMalloc(&r->q.next, (size_t)cap * 4));
-  IZ_CUDA(cudaMalloc(&r->q.bins, (size_t)cap * 4 * kClasses));
-  IZ_CUDA(cudaMalloc(&r->q.counters, 16 * sizeof(unsigned long long)));
-  r->q.capacity = cap;
-  IZ_CUDA(cudaHostAlloc(&r->h_count, sizeof(unsigned long long), cudaHostAllocMapped));
-  IZ_CUDA(cudaHostGetDevicePointer(&r->d_count_mapped, r->h_count, 0));
+  if (!r->d_paths) {
+    int32_t cap = r->batch_paths;
+    IZ_CUDA(cudaMalloc(&r->d_paths, (size_t)cap * sizeof(PathState)));
+    IZ_CUDA(cudaMalloc(&r->q.cur, (size_t)cap * 4));
+    IZ_CUDA(cudaMalloc(&r->q.next, (size_t)cap * 4));
+    IZ_CUDA(cudaMalloc(&r->q.bins, (size_t)cap * 4 * kClasses));
+    IZ_CUDA(cudaMalloc(&r->q.counters, 16 * sizeof(unsigned long long)));
+    r->q.capacity = cap;
+    IZ_CUDA(cudaHostAlloc(&r->h_count, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
+    IZ_CUDA(cudaHostGetDevicePointer(&r->d_count_mapped, r->h_count, 0));
+    IZ_CUDA(cudaEventCreateWithFlags(&r->ev[0], cudaEventDisableTiming));
+    IZ_CUDA(cudaEventCreateWithFlags(&r->ev[1], cudaEventDisableTiming));
+  }
   IZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return IZPI_OK;
 }

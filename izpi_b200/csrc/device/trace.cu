@@ -55,13 +55,16 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads)
 trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __restrict__ org,
                 const double* __restrict__ dir, double tmin, double tmax, int32_t* __restrict__ ids,
-                double* __restrict__ ts, unsigned long long* counters) {
+                double* __restrict__ ts, unsigned long long* counters, int stragglers) {
   extern __shared__ int2 g4_stack_smem[];  // [rays per block][kG4Stack + 1]: one private stack per ray
   const unsigned lane = threadIdx.x & 31u;
   const int g = lane >> 2, j = lane & 3;
   const int gshift = g * 4;
   const unsigned gmask = 0xfu << gshift;
   int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 2) * (kG4Stack + 1);
+  const long long warps = (long long)gridDim.x * (kTraceThreads / 32);
+  long long chunk = (n / (warps * 4) + 7) & ~7ll;  // rays per atomicAdd: shrinks for small batches (tail balance)
+  chunk = chunk < 8 ? 8 : (chunk > kChunk ? kChunk : chunk);
   uint32_t n_nodes = 0, n_prims = 0;
   long long chunk_next = 0, chunk_end = 0;  // warp-uniform
   bool exhausted = false;
@@ -74,10 +77,10 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
     if (idle) {
       if (chunk_next >= chunk_end && !exhausted) {
         long long b = 0;
-        if (lane == 0) b = (long long)atomicAdd(&counters[0], (unsigned long long)kChunk);
+        if (lane == 0) b = (long long)atomicAdd(&counters[0], (unsigned long long)chunk);
         b = __shfl_sync(0xffffffffu, b, 0);
         chunk_next = b;
-        chunk_end = b + kChunk < n ? b + kChunk : n;
+        chunk_end = b + chunk < n ? b + chunk : n;
         if (b >= n) { exhausted = true; chunk_next = chunk_end = 0; }
       }
       int before = __popc(idle & ((1u << gshift) - 1u)) >> 2;  // idle groups ahead of mine
@@ -96,7 +99,7 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
       if (exhausted && __ballot_sync(0xffffffffu, s.cur == kIdle) == 0xffffffffu) break;
     }
     // ---- node phase, then leaf phase (both warp-uniform)
-    g4_node_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes);
+    g4_node_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, stragglers);
     g4_leaf_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, n_prims);
     // ---- finished rays write their answer
     if (s.cur == kIdle && ray >= 0) {
@@ -142,7 +145,8 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
     long long grid4 = (long long)ctx->sm_count * bps4;
     if (grid4 > want4) grid4 = want4;
     if (grid4 < 1) grid4 = 1;
-    k4<<<(unsigned)grid4, kTraceThreads, smem4, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, ctx->d_counters);
+    k4<<<(unsigned)grid4, kTraceThreads, smem4, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, ctx->d_counters,
+                                                        ctx->node_stragglers);
     IZ_CUDA(cudaGetLastError());
     ctx->launches++;
     return IZPI_OK;
