@@ -89,6 +89,29 @@ def cpu_baseline(sc, lo, hi, n_sample, threads):
     return n_sample / dt / 1e6, st, (ids, t, org, d)
 
 
+def bench_render(ctx, cuda, scenes, world, rank, barrier):
+    """Second half of BASELINE's metric: Msamples/s of the tile renderer, end to end through
+    render.New(...).Render() (setup, tiles, NCCL reduce of the fp64 canvas for N>1, epilogue, D2H).
+    Strong scaling: the image is fixed, its tiles are dealt to the ranks."""
+    import time as _t
+    from izpi_b200 import render
+    out = []
+    for name, spec, w, h, spp, sampler in (
+            ("config 1: cornell box 400x400, 64 spp, colour", scenes.cornell_box(1.0), 400, 400, 64, cuda.SAMPLER_COLOUR),
+            ("config 4 scene: spectral glass pyramid 1024x1024 at 16 spp (BASELINE: 1024 spp)", scenes.spectral_pyramid(1.0), 1024, 1024, 16, cuda.SAMPLER_SPECTRAL)):
+        ctx.upload(cuda.HostScene(spec))
+        r = render.New(ctx, w, h, spp, 50, sampler_type=sampler, seed=3)
+        render.New(ctx, w, h, 1, 50, sampler_type=sampler, seed=3).Render()  # warm-up
+        barrier()
+        t0 = _t.perf_counter()
+        r.Render()
+        barrier()
+        dt = _t.perf_counter() - t0
+        out.append({"scene": name, "msamples_per_s": w * h * spp / dt / 1e6, "seconds": dt, "scaling": "strong",
+                    "mrays_per_s": (r.num_rays / dt / 1e6) if rank == 0 else None})
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -212,6 +235,9 @@ def main():
     # results of the two paths agree
     assert np.array_equal(np_ids, d_ids.cpu().numpy()) and np.array_equal(np_t, d_t.cpu().numpy())
 
+    render_info = bench_render(ctx, cuda, scenes, world, rank, barrier)
+    ctx.upload(hs)  # back to the closest-hit scene for the CPU-baseline parity check below
+
     if world > 1:
         tt = torch.tensor([total_ms, e2e_ms, kernel_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -233,6 +259,7 @@ def main():
             "e2e": {"value": world * n * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 48,
                     "d2h_bytes_per_step": n * 12},
             "gpu_launches": int(launches),
+            "render": render_info,
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:

@@ -1,0 +1,88 @@
+"""Host-side render logic that needs no GPU: the tile grid (common.Tiles, renderer.go:116,172-188), the
+round-robin shard across ranks, and the one-reduce exchange step (world_size 2 over gloo on CPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from izpi_b200 import render
+from izpi_b200.build import build as build_lib
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    build_lib()
+
+
+@pytest.mark.parametrize("w,h,tile", [(400, 400, (25, 25)), (1024, 1024, (32, 32)), (3840, 2160, (32, 24)), (40, 60, (20, 20))])
+def test_tile_list_covers_image_once(w, h, tile):
+    t = render.tile_list(w, h)
+    assert len(t) == (w // tile[0]) * (h // tile[1])
+    assert ((t[:, 2] - t[:, 0] + 1) == tile[0]).all() and ((t[:, 3] - t[:, 1] + 1) == tile[1]).all()
+    cover = np.zeros((h, w), dtype=np.int32)
+    for x0, y0, x1, y1 in t[:: max(1, len(t) // 400)]:
+        cover[y0:y1 + 1, x0:x1 + 1] += 1
+    assert cover.max() == 1
+    area = ((t[:, 2] - t[:, 0] + 1).astype(np.int64) * (t[:, 3] - t[:, 1] + 1)).sum()
+    assert area == w * h
+    # 4K case of BASELINE config 5: 10 800 tiles
+    if (w, h) == (3840, 2160):
+        assert len(t) == 10800
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shards_partition_tiles(world):
+    t = render.tile_list(1024, 1024)
+    parts = [render.shard_tiles(t, world, r) for r in range(world)]
+    assert sum(len(p) for p in parts) == len(t)
+    allrows = np.concatenate(parts)
+    assert len(np.unique(allrows, axis=0)) == len(t)
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_tiles_error_when_nothing_divides():
+    from izpi_b200 import cuda
+    with pytest.raises(cuda.IzpiError):
+        render.tile_list(17, 16)
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = h = 64
+    tiles = render.tile_list(w, h)
+    mine = render.shard_tiles(tiles, world, rank)
+    # stand-in for izpi_render_tiles: every pixel of my tiles gets a value that depends only on (x, y)
+    canvas = torch.zeros((h, w, 4), dtype=torch.float64)
+    for x0, y0, x1, y1 in mine:
+        ys, xs = torch.meshgrid(torch.arange(int(y0), int(y1) + 1), torch.arange(int(x0), int(x1) + 1), indexing="ij")
+        canvas[int(y0):int(y1) + 1, int(x0):int(x1) + 1, 0] = (xs * 0.1 + ys * 7.3).double()
+        canvas[int(y0):int(y1) + 1, int(x0):int(x1) + 1, 3] = 1.0
+    render.reduce_canvas(canvas, dst=0)
+    if rank == 0:
+        ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        want = (xs * 0.1 + ys * 7.3).double()
+        q.put(bool(torch.equal(canvas[..., 0], want) and bool((canvas[..., 3] == 1).all())))
+    dist.destroy_process_group()
+
+
+def test_reduce_canvas_world2_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
