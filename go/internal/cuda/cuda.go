@@ -1,0 +1,155 @@
+// Package cuda binds libizpi_cuda.so (include/izpi_cuda.h) for Izpi's render loop.
+//
+// NOT COMPILED IN THIS REPOSITORY'S ENVIRONMENT (no Go toolchain in the image).  It is the cgo stub a
+// maintainer adds to flynn-nrg/izpi as internal/cuda; INTEGRATION.md explains where each call goes.
+//
+// Threading: one goroutine per GPU, pinned with runtime.LockOSThread (CUDA context affinity); calls on
+// one Context are serialised by that goroutine.  C never retains a Go pointer: uploads copy, outputs
+// are Go-allocated slices that live for the duration of the call.
+package cuda
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../../izpi_b200 -lizpi_cuda -Wl,-rpath,${SRCDIR}/../../../izpi_b200
+#include "izpi_cuda.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"runtime"
+	"unsafe"
+)
+
+// Context is one GPU.
+type Context struct{ h *C.izpi_ctx }
+
+func lastError(op string, rc C.int) error {
+	return fmt.Errorf("izpi cuda: %s: %s (code %d)", op, C.GoString(C.izpi_last_error()), int(rc))
+}
+
+// NewContext opens device `dev`.  Call from the goroutine that will own it.
+func NewContext(dev int) (*Context, error) {
+	runtime.LockOSThread()
+	id := C.int(dev)
+	var h *C.izpi_ctx
+	if rc := C.izpi_ctx_create(1, &id, &h); rc != 0 {
+		return nil, lastError("izpi_ctx_create", rc)
+	}
+	return &Context{h: h}, nil
+}
+
+func (c *Context) Close() { C.izpi_ctx_destroy(c.h); c.h = nil }
+
+// SceneDesc is built by package hitable (Flatten, see INTEGRATION.md) from scene.Scene.
+type SceneDesc struct {
+	WorldKind  int32
+	Nodes      []C.izpi_bvh4_node // hitable.BVH4.Nodes reinterpreted: identical 128-byte layout
+	Prims      []C.izpi_prim_rec
+	TriAttrs   []C.izpi_tri_attr
+	Xforms     []C.izpi_xform
+	Lights     []int32
+	Materials  []C.izpi_material_spec
+	Textures   []C.izpi_texture_spec
+	Spectral   []C.izpi_spectral_texture_spec
+	Camera     C.izpi_camera
+	HasWorld   bool
+	pin        runtime.Pinner // keeps texture pixel slices addressable during Upload
+}
+
+func ptr[T any](s []T) *T {
+	if len(s) == 0 {
+		return nil
+	}
+	return &s[0]
+}
+
+// Upload copies the flattened scene to the GPU (replaces nothing in the reference: the CPU path keeps
+// its object graph; this is the additional one-off step after transport.ToScene()).
+func (c *Context) Upload(d *SceneDesc) error {
+	var cd C.izpi_scene_desc
+	cd.world_kind = C.int32_t(d.WorldKind)
+	cd.n_nodes, cd.nodes = C.int32_t(len(d.Nodes)), ptr(d.Nodes)
+	cd.n_prims, cd.prims, cd.tri_attrs = C.int32_t(len(d.Prims)), ptr(d.Prims), ptr(d.TriAttrs)
+	cd.n_xforms, cd.xforms = C.int32_t(len(d.Xforms)), ptr(d.Xforms)
+	cd.n_lights, cd.lights = C.int32_t(len(d.Lights)), (*C.int32_t)(unsafe.Pointer(ptr(d.Lights)))
+	cd.n_materials, cd.materials = C.int32_t(len(d.Materials)), ptr(d.Materials)
+	cd.n_textures, cd.textures = C.int32_t(len(d.Textures)), ptr(d.Textures)
+	cd.n_spectral_textures, cd.spectral_textures = C.int32_t(len(d.Spectral)), ptr(d.Spectral)
+	cd.camera = d.Camera
+	if d.HasWorld {
+		cd.dielectric_has_world = 1
+	}
+	defer d.pin.Unpin()
+	if rc := C.izpi_scene_upload(c.h, &cd); rc != 0 {
+		return lastError("izpi_scene_upload", rc)
+	}
+	return nil
+}
+
+// TraceClosest is hitable.Hitable.Hit for a batch: origins/directions are xyz-interleaved float64.
+// ids[i] is the index of the hit primitive in the ORIGINAL hitables list (-1 = miss).
+func (c *Context) TraceClosest(org, dir []float64, tMin, tMax float64, ids []int32, t []float64) error {
+	n := len(ids)
+	if len(org) != 3*n || len(dir) != 3*n || len(t) != n {
+		return fmt.Errorf("izpi cuda: TraceClosest: slice lengths disagree")
+	}
+	if n == 0 {
+		return nil
+	}
+	rc := C.izpi_trace_closest(c.h, C.int64_t(n), (*C.double)(&org[0]), (*C.double)(&dir[0]), C.double(tMin), C.double(tMax),
+		C.IZPI_TRACE_EXACT, (*C.int32_t)(&ids[0]), (*C.double)(&t[0]), nil)
+	if rc != 0 {
+		return lastError("izpi_trace_closest", rc)
+	}
+	return nil
+}
+
+// RenderConfig mirrors the arguments of render.New (renderer.go:73-88).
+type RenderConfig struct {
+	Width, Height, Samples, MaxDepth int
+	Spectral                         bool
+	Background                       [3]float64
+	BgWavelengths, BgValues          []float64
+	Seed                             uint64
+}
+
+func (c *Context) RenderSetup(rc RenderConfig) error {
+	var cc C.izpi_render_config
+	cc.width, cc.height, cc.spp, cc.max_depth = C.int32_t(rc.Width), C.int32_t(rc.Height), C.int32_t(rc.Samples), C.int32_t(rc.MaxDepth)
+	if rc.Spectral {
+		cc.sampler = C.IZPI_SAMPLER_SPECTRAL
+	}
+	cc.sample_count = cc.spp
+	for i := 0; i < 3; i++ {
+		cc.background[i] = C.double(rc.Background[i])
+	}
+	if len(rc.BgWavelengths) > 0 {
+		cc.bg_wavelengths, cc.bg_values, cc.n_bg = (*C.double)(&rc.BgWavelengths[0]), (*C.double)(&rc.BgValues[0]), C.int32_t(len(rc.BgWavelengths))
+	}
+	cc.seed = C.uint64_t(rc.Seed)
+	if r := C.izpi_render_setup(c.h, &cc); r != 0 {
+		return lastError("izpi_render_setup", r)
+	}
+	return nil
+}
+
+// RenderTiles renders a batch of workUnits {x0,y0,x1,y1} (renderer.go:183-186).
+func (c *Context) RenderTiles(tiles []uint32) error {
+	if len(tiles) == 0 {
+		return nil
+	}
+	if r := C.izpi_render_tiles(c.h, C.int32_t(len(tiles)/4), (*C.uint32_t)(&tiles[0]), nil); r != 0 {
+		return lastError("izpi_render_tiles", r)
+	}
+	return nil
+}
+
+// RenderFinish returns the canvas (Float64NRGBA.Pix layout) and the ray total (renderer.go:213-221).
+func (c *Context) RenderFinish(pix []float64) (uint64, error) {
+	var rays C.uint64_t
+	if r := C.izpi_render_finish(c.h, (*C.double)(&pix[0]), &rays); r != 0 {
+		return 0, lastError("izpi_render_finish", r)
+	}
+	return uint64(rays), nil
+}
