@@ -54,6 +54,7 @@ int izpi_ctx_create(int n_devices, const int* device_ids, izpi_ctx** out) {
   IZ_CUDA(cudaGetDeviceProperties(&prop, dev));
   ctx->sm_count = prop.multiProcessorCount;
   IZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  IZ_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   IZ_CUDA(cudaEventCreate(&ctx->ev0));
   IZ_CUDA(cudaEventCreate(&ctx->ev1));
   IZ_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
@@ -72,6 +73,7 @@ void izpi_ctx_destroy(izpi_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
 }
 

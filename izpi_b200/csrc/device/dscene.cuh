@@ -59,6 +59,7 @@ struct izpi_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second lane of the copy/compute pipeline of izpi_trace_closest
   bool has_scene = false;
   int node_stragglers = 4;    // IZPI_NODE_STRAGGLERS: node-phase exit threshold of the 4-lanes-per-ray kernels
   bool force_scalar = false;  // IZPI_FORCE_SCALAR=1: thread-per-ray traversal even for reference-shaped trees

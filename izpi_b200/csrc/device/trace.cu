@@ -50,9 +50,12 @@ trace_kernel(const __grid_constant__ DScene sc, long long n, const double* __res
 // atomicAdd per chunk), handed to idle groups as they finish (persistent threads with ray replacement),
 // and the warp alternates between a node phase and a leaf phase (intersect_g4.cuh).
 constexpr int kChunk = 256;
+#ifndef IZPI_G4_MIN_BLOCKS
+#define IZPI_G4_MIN_BLOCKS 5
+#endif
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, IZPI_G4_MIN_BLOCKS)
 trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __restrict__ org,
                 const double* __restrict__ dir, double tmin, double tmax, int32_t* __restrict__ ids,
                 double* __restrict__ ts, unsigned long long* counters, int stragglers) {
@@ -130,9 +133,9 @@ __global__ void box4_kernel(int n, const float* __restrict__ org, const float* _
 }
 
 int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir, double tmin, double tmax,
-                 int mode, int32_t* d_ids, double* d_t, cudaStream_t st, bool count) {
+                 int mode, int32_t* d_ids, double* d_t, cudaStream_t st, bool count, unsigned long long* counters) {
   if (mode != IZPI_TRACE_EXACT) { set_error("izpi_trace_closest: only IZPI_TRACE_EXACT is implemented"); return IZPI_EINVAL; }
-  IZ_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(unsigned long long), st));
+  IZ_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), st));
   if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar) {
     size_t smem4 = (size_t)(kTraceThreads / 4) * (kG4Stack + 1) * sizeof(int2);
     auto k4 = count ? trace_g4_kernel<true> : trace_g4_kernel<false>;
@@ -145,7 +148,7 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
     long long grid4 = (long long)ctx->sm_count * bps4;
     if (grid4 > want4) grid4 = want4;
     if (grid4 < 1) grid4 = 1;
-    k4<<<(unsigned)grid4, kTraceThreads, smem4, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, ctx->d_counters,
+    k4<<<(unsigned)grid4, kTraceThreads, smem4, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, counters,
                                                         ctx->node_stragglers);
     IZ_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -165,7 +168,7 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, kTraceThreads, smem, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t,
-                                                     ctx->d_counters);
+                                                     counters);
   IZ_CUDA(cudaGetLastError());
   ctx->launches++;
   return IZPI_OK;
@@ -181,7 +184,8 @@ int izpi_trace_closest_device(izpi_ctx* ctx, int64_t n, const double* d_org, con
   if (!ctx->has_scene) { set_error("izpi_trace_closest_device: no scene uploaded"); return IZPI_ESTATE; }
   if (n == 0) return IZPI_OK;
   IZ_CUDA(cudaSetDevice(ctx->device));
-  return launch_trace(ctx, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, stream ? (cudaStream_t)stream : ctx->stream, false);
+  return launch_trace(ctx, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, stream ? (cudaStream_t)stream : ctx->stream, false,
+                      ctx->d_counters);
 }
 
 int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double* dir, double tmin, double tmax, int mode,
@@ -200,30 +204,44 @@ int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double
     IZ_CUDA(cudaMalloc(&ctx->d_t, (size_t)n * 8));
     ctx->ray_capacity = n;
   }
-  cudaStream_t st = ctx->stream;
-  // The batch is cut into slices so the copies of slice k+1 / k-1 overlap the traversal of slice k
-  // (pinned host buffers make the copies truly asynchronous; pageable ones still work).
-  const int64_t slice = 1 << 20;
-  IZ_CUDA(cudaEventRecord(ctx->ev0, st));
-  for (int64_t b = 0; b < n; b += slice) {
-    int64_t m = n - b < slice ? n - b : slice;
-    IZ_CUDA(cudaMemcpyAsync(ctx->d_org + 3 * b, org + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, st));
-    IZ_CUDA(cudaMemcpyAsync(ctx->d_dir + 3 * b, dir + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, st));
-  }
-  int rc = launch_trace(ctx, n, ctx->d_org, ctx->d_dir, tmin, tmax, mode, ctx->d_ids, ctx->d_t, st, stats != nullptr);
-  if (rc != IZPI_OK) return rc;
-  IZ_CUDA(cudaEventRecord(ctx->ev1, st));
-  IZ_CUDA(cudaMemcpyAsync(prim_id, ctx->d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  IZ_CUDA(cudaMemcpyAsync(t, ctx->d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  IZ_CUDA(cudaStreamSynchronize(st));
-  if (stats) {
+  if (stats) {  // counting run: one launch on one stream
+    cudaStream_t st = ctx->stream;
+    IZ_CUDA(cudaMemcpyAsync(ctx->d_org, org, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    IZ_CUDA(cudaMemcpyAsync(ctx->d_dir, dir, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    IZ_CUDA(cudaEventRecord(ctx->ev0, st));
+    int rc = launch_trace(ctx, n, ctx->d_org, ctx->d_dir, tmin, tmax, mode, ctx->d_ids, ctx->d_t, st, true, ctx->d_counters);
+    if (rc != IZPI_OK) return rc;
+    IZ_CUDA(cudaEventRecord(ctx->ev1, st));
+    IZ_CUDA(cudaMemcpyAsync(prim_id, ctx->d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    IZ_CUDA(cudaMemcpyAsync(t, ctx->d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    IZ_CUDA(cudaStreamSynchronize(st));
     unsigned long long c[3];
     IZ_CUDA(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
     stats->rays = (uint64_t)n; stats->nodes_visited = c[1]; stats->prim_tests = c[2];
     float ms = 0;
     IZ_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    stats->kernel_ms = ms;  // includes the H2D copies queued ahead of the kernel
+    stats->kernel_ms = ms;
+    return IZPI_OK;
   }
+  // The batch is cut into slices that alternate between two streams: while slice k is traversed, the rays of
+  // slice k+1 arrive over PCIe and the answers of slice k-1 leave (the copies are truly asynchronous when the
+  // caller's buffers are pinned; pageable buffers still work, just without the overlap).
+  const int64_t slice = 1 << 21;
+  cudaStream_t ss[2] = {ctx->stream, ctx->stream2};
+  int k = 0;
+  for (int64_t b = 0; b < n; b += slice, k ^= 1) {
+    int64_t m = n - b < slice ? n - b : slice;
+    cudaStream_t st = ss[k];
+    IZ_CUDA(cudaMemcpyAsync(ctx->d_org + 3 * b, org + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, st));
+    IZ_CUDA(cudaMemcpyAsync(ctx->d_dir + 3 * b, dir + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, st));
+    int rc = launch_trace(ctx, m, ctx->d_org + 3 * b, ctx->d_dir + 3 * b, tmin, tmax, mode, ctx->d_ids + b, ctx->d_t + b, st, false,
+                          ctx->d_counters + 4 * k);
+    if (rc != IZPI_OK) return rc;
+    IZ_CUDA(cudaMemcpyAsync(prim_id + b, ctx->d_ids + b, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    IZ_CUDA(cudaMemcpyAsync(t + b, ctx->d_t + b, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+  }
+  IZ_CUDA(cudaStreamSynchronize(ss[0]));
+  IZ_CUDA(cudaStreamSynchronize(ss[1]));
   return IZPI_OK;
 }
 
