@@ -133,3 +133,10 @@ def test_render_errors(ctx):
     ctx.upload(cuda.HostScene(scenes.cornell_box(1.0)))
     with pytest.raises(cuda.IzpiError):  # common.Tiles finds no divisor (the reference divides by zero)
         ctx.render(17, 16, 1)
+
+
+def test_ibl_metal_mesh_same_path(ctx, oracle_mod):
+    """Config 5 materials/geometry at test size: sky dome = FlipNormals(Sphere) with an image DiffuseLight,
+    Metal mesh, glass sphere; all specular, as in scenes.Environment."""
+    sc = scenes.ibl_displaced_mesh(16 / 9, 120, 60, (256, 128))
+    _same_path(ctx, oracle_mod, sc, 64, 36, 8, cuda.SAMPLER_COLOUR, min_close=0.97)
