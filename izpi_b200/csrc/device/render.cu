@@ -559,33 +559,57 @@ __global__ void xyz_to_acescg_kernel(double* pix, long long n_px, double exposur
 }  // namespace
 
 // ---- host side of the render entry points -------------------------------------------------------
+// Work is cut into batches of (pixel block x sample block) paths.  kSlots batches are in flight at once,
+// each on its own stream with its own path/queue buffers: while one batch runs its long tail of
+// nearly empty bounces (paths caught between glass and metal live up to maxDepth = 50 bounces), the next
+// one fills the SMs with its first, wide bounces.  Resolves are chained in batch order, so every pixel
+// still adds its samples in the reference's order and the canvas is independent of the overlap.
+constexpr int kSlots = 2;
+constexpr int kMaxBounces = 4096;
+
+__global__ void accumulate_traced_kernel(const unsigned long long* counters, unsigned long long* total) { *total += counters[8]; }
+
+struct BatchSlot {
+  PathState* d_paths = nullptr;
+  Queues q{};
+  uint32_t* d_pixels = nullptr;
+  int64_t pixel_capacity = 0;
+  unsigned long long* h_count = nullptr;  // pinned + mapped: advance_kernel writes the live count of bounce b to [b & 7]
+  unsigned long long* d_count_mapped = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t resolved = nullptr;
+  // run state
+  bool busy = false, drained = false;
+  int batch = -1, n_pixels = 0, s_begin = 0, s_count = 0, bounce = 0;
+  unsigned long long live = 0;
+};
+
 struct RenderState {
   izpi_render_config cfg{};
   RenderParams rp{};
   double* d_canvas = nullptr;   // running sums, 4*W*H
   double* d_out = nullptr;      // means / epilogue scratch
   double* d_snap = nullptr;
-  PathState* d_paths = nullptr;
-  uint32_t* d_pixels = nullptr;
-  int64_t pixel_capacity = 0;
-  Queues q{};
-  double* d_bg = nullptr;
-  unsigned long long* h_count = nullptr;  // pinned, written by advance_kernel
-  unsigned long long* d_count_mapped = nullptr;
-  uint64_t total_rays = 0;
-  int32_t batch_paths = 1 << 23;  // 8M paths x 160 B = 1.3 GB of HBM
   size_t canvas_capacity = 0;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  double* d_bg = nullptr;
+  unsigned long long* d_total_rays = nullptr;
+  BatchSlot slot[kSlots];
+  int32_t batch_paths = 1 << 24;  // paths per batch: 16M x 160 B = 2.7 GB of HBM per slot
+  bool allocated = false;
 };
 
 void render_state_free(izpi_ctx* ctx) {
   RenderState* r = ctx->render;
   if (!r) return;
-  cudaFree(r->d_canvas); cudaFree(r->d_out); cudaFree(r->d_snap); cudaFree(r->d_paths); cudaFree(r->d_pixels);
-  cudaFree(r->q.cur); cudaFree(r->q.next); cudaFree(r->q.bins); cudaFree(r->q.counters); cudaFree(r->d_bg);
-  if (r->h_count) cudaFreeHost(r->h_count);
-  if (r->ev[0]) cudaEventDestroy(r->ev[0]);
-  if (r->ev[1]) cudaEventDestroy(r->ev[1]);
+  cudaFree(r->d_canvas); cudaFree(r->d_out); cudaFree(r->d_snap); cudaFree(r->d_bg); cudaFree(r->d_total_rays);
+  for (BatchSlot& s : r->slot) {
+    cudaFree(s.d_paths); cudaFree(s.d_pixels); cudaFree(s.q.cur); cudaFree(s.q.next); cudaFree(s.q.bins); cudaFree(s.q.counters);
+    if (s.h_count) cudaFreeHost(s.h_count);
+    for (cudaEvent_t e : s.ev) if (e) cudaEventDestroy(e);
+    if (s.resolved) cudaEventDestroy(s.resolved);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
   delete r;
   ctx->render = nullptr;
 }
@@ -603,74 +627,107 @@ int upload_cie() {
 }
 
 template <typename K, typename... Args>
-int launch(izpi_ctx* ctx, K kern, dim3 grid, dim3 block, size_t smem, Args... args) {
-  kern<<<grid, block, smem, ctx->stream>>>(args...);
+int launch(izpi_ctx* ctx, cudaStream_t st, K kern, dim3 grid, dim3 block, size_t smem, Args... args) {
+  kern<<<grid, block, smem, st>>>(args...);
   IZ_CUDA(cudaGetLastError());
   ctx->launches++;
   return IZPI_OK;
 }
 
-int render_batch(izpi_ctx* ctx, RenderState* r, int n_pixels, int s_begin, int s_count) {
-  cudaStream_t st = ctx->stream;
-  const int sm = ctx->sm_count;
-  IZ_CUDA(cudaMemsetAsync(r->q.counters, 0, 9 * sizeof(unsigned long long), st));
-  long long n = (long long)n_pixels * s_count;
-  int rc;
-  int gen_grid = (int)std::min<long long>((n + 255) / 256, (long long)sm * 8);
-  if ((rc = launch(ctx, raygen_kernel, dim3(gen_grid), dim3(256), 0, ctx->scene, r->rp, r->d_paths, r->d_pixels, n_pixels,
-                   s_begin, s_count, r->q)) != IZPI_OK) return rc;
-  size_t smem = (size_t)kStackDepth * kThreads * sizeof(int32_t);
-  static thread_local int ext_blocks = 0;
+struct LaunchCfg {
+  bool use_g4;
+  size_t smem, smem4;
+  int ext_blocks, ext4_blocks;
+};
+
+int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
+  lc.smem = (size_t)kStackDepth * kThreads * sizeof(int32_t);
+  lc.smem4 = (size_t)(kThreads / 4) * (kG4Stack + 1) * sizeof(int2);
+  static thread_local int ext_blocks = 0, ext4_blocks = 0;
   if (!ext_blocks) {
-    IZ_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_blocks, extend_kernel, kThreads, smem));
+    IZ_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_blocks, extend_kernel, kThreads, lc.smem));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext4_blocks, extend_g4_kernel, kThreads, lc.smem4));
     if (ext_blocks < 1) ext_blocks = 1;
-  }
-  // tiny trees (config 4 has 22 primitives) stay cache-resident and coherent: the thread-per-ray stage wins there
-  const bool use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= 64;
-  const size_t smem4 = (size_t)(kThreads / 4) * (kG4Stack + 1) * sizeof(int2);
-  static thread_local int ext4_blocks = 0;
-  if (!ext4_blocks) {
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext4_blocks, extend_g4_kernel, kThreads, smem4));
     if (ext4_blocks < 1) ext4_blocks = 1;
   }
-  // The live-path count of bounce b is read back while bounce b+1 is already queued: the host never
-  // stalls the GPU between bounces.  Counts only shrink, so a stale count is a valid upper bound for
-  // grid sizing, and the loop stops one (empty) bounce after the queue ran dry.
-  unsigned long long live = (unsigned long long)n;
-  for (int bounce = 0; bounce <= r->rp.max_depth; bounce++) {
-    long long want = ((long long)live + kThreads - 1) / kThreads;
-    int eg = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * ext_blocks));
-    if (use_g4) {
-      long long want4 = ((long long)live + (kThreads / 4) - 1) / (kThreads / 4);
-      int eg4 = (int)std::max<long long>(1, std::min<long long>(want4, (long long)sm * ext4_blocks));
-      if ((rc = launch(ctx, extend_g4_kernel, dim3(eg4), dim3(kThreads), smem4, ctx->scene, r->rp, r->d_paths, r->q,
-                       ctx->node_stragglers)) != IZPI_OK) return rc;
-    } else if ((rc = launch(ctx, extend_kernel, dim3(eg), dim3(kThreads), smem, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) {
-      return rc;
-    }
-    int sg = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * 8));
-    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_LAMBERT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
-    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_METAL>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
-    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_DIELECTRIC>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
-    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_DIFFUSE_LIGHT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
-    if ((rc = launch(ctx, shade_kernel<IZPI_MAT_PBR>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, r->d_paths, r->q)) != IZPI_OK) return rc;
-    std::swap(r->q.cur, r->q.next);
-    Queues qs = r->q;  // after the swap: cur = survivors; advance moves the count
-    if ((rc = launch(ctx, advance_kernel, dim3(1), dim3(1), 0, qs, r->d_count_mapped + (bounce & 1))) != IZPI_OK) return rc;
-    IZ_CUDA(cudaEventRecord(r->ev[bounce & 1], st));
-    if (bounce >= 1) {
-      IZ_CUDA(cudaEventSynchronize(r->ev[(bounce - 1) & 1]));
-      live = r->h_count[(bounce - 1) & 1];
-      if (live == 0) break;
-    }
+  lc.ext_blocks = ext_blocks; lc.ext4_blocks = ext4_blocks;
+  // tiny trees (config 4 has 22 primitives) stay cache-resident and coherent: the thread-per-ray stage wins there
+  lc.use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= 64;
+  return IZPI_OK;
+}
+
+// first launches of a batch: pixel list, counters, ray generation
+int batch_start(izpi_ctx* ctx, RenderState* r, BatchSlot& s, int batch, const uint32_t* px, int n_pixels, int s_begin, int s_count) {
+  cudaStream_t st = s.stream;
+  if (n_pixels > s.pixel_capacity) {
+    IZ_CUDA(cudaStreamSynchronize(st));
+    cudaFree(s.d_pixels); s.d_pixels = nullptr; s.pixel_capacity = 0;
+    IZ_CUDA(cudaMalloc(&s.d_pixels, (size_t)n_pixels * 4));
+    s.pixel_capacity = n_pixels;
   }
-  if ((rc = launch(ctx, resolve_kernel, dim3((n_pixels + 127) / 128), dim3(128), 0, r->rp, r->d_paths, r->d_pixels, n_pixels,
-                   s_count, r->d_canvas)) != IZPI_OK) return rc;
-  unsigned long long traced = 0;
-  IZ_CUDA(cudaMemcpyAsync(&traced, r->q.counters + 8, sizeof(traced), cudaMemcpyDeviceToHost, st));
-  IZ_CUDA(cudaStreamSynchronize(st));
-  r->total_rays += traced;
+  IZ_CUDA(cudaMemcpyAsync(s.d_pixels, px, (size_t)n_pixels * 4, cudaMemcpyHostToDevice, st));
+  IZ_CUDA(cudaMemsetAsync(s.q.counters, 0, 9 * sizeof(unsigned long long), st));
+  long long n = (long long)n_pixels * s_count;
+  int gen_grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
+  int rc = launch(ctx, st, raygen_kernel, dim3(gen_grid), dim3(256), 0, ctx->scene, r->rp, s.d_paths, s.d_pixels, n_pixels, s_begin,
+                  s_count, s.q);
+  if (rc != IZPI_OK) return rc;
+  s.busy = true; s.drained = false; s.batch = batch; s.n_pixels = n_pixels; s.s_begin = s_begin; s.s_count = s_count;
+  s.bounce = 0; s.live = (unsigned long long)n;
+  return IZPI_OK;
+}
+
+// One bounce of a batch.  The live count of bounce b-2 is harvested first (the host runs at most two bounces ahead
+// of the device); counts only shrink, so the stale value is a valid upper bound for the grid size.
+int batch_step(izpi_ctx* ctx, RenderState* r, BatchSlot& s, const LaunchCfg& lc) {
+  cudaStream_t st = s.stream;
+  const int sm = ctx->sm_count;
+  if (s.bounce >= 2) {
+    IZ_CUDA(cudaEventSynchronize(s.ev[(s.bounce - 2) & 7]));
+    s.live = s.h_count[(s.bounce - 2) & 7];
+  }
+  if (s.live == 0 || s.bounce > r->rp.max_depth || s.bounce >= kMaxBounces) { s.drained = true; return IZPI_OK; }
+  int rc;
+  long long want = ((long long)s.live + kThreads - 1) / kThreads;
+  if (lc.use_g4) {
+    long long want4 = ((long long)s.live + (kThreads / 4) - 1) / (kThreads / 4);
+    int eg4 = (int)std::max<long long>(1, std::min<long long>(want4, (long long)sm * lc.ext4_blocks));
+    if ((rc = launch(ctx, st, extend_g4_kernel, dim3(eg4), dim3(kThreads), lc.smem4, ctx->scene, r->rp, s.d_paths, s.q,
+                     ctx->node_stragglers)) != IZPI_OK) return rc;
+  } else {
+    int eg = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * lc.ext_blocks));
+    if ((rc = launch(ctx, st, extend_kernel, dim3(eg), dim3(kThreads), lc.smem, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
+  }
+  int sg = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * 8));
+  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_LAMBERT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
+  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_METAL>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
+  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_DIELECTRIC>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
+  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_DIFFUSE_LIGHT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
+  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_PBR>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
+  std::swap(s.q.cur, s.q.next);
+  Queues qs = s.q;  // after the swap: cur = survivors; advance moves the count
+  if ((rc = launch(ctx, st, advance_kernel, dim3(1), dim3(1), 0, qs, s.d_count_mapped + (s.bounce & 7))) != IZPI_OK) return rc;
+  IZ_CUDA(cudaEventRecord(s.ev[s.bounce & 7], st));
+  s.bounce++;
+  return IZPI_OK;
+}
+
+// last launches of a batch: per-pixel sums in sample order, after the previous batch's resolve
+int batch_finish(izpi_ctx* ctx, RenderState* r, BatchSlot& s, cudaEvent_t prev_resolved) {
+  cudaStream_t st = s.stream;
+  if (prev_resolved) IZ_CUDA(cudaStreamWaitEvent(st, prev_resolved, 0));
+  int rc = launch(ctx, st, resolve_kernel, dim3((s.n_pixels + 127) / 128), dim3(128), 0, r->rp, s.d_paths, s.d_pixels, s.n_pixels,
+                  s.s_count, r->d_canvas);
+  if (rc != IZPI_OK) return rc;
+  if ((rc = launch(ctx, st, accumulate_traced_kernel, dim3(1), dim3(1), 0, s.q.counters, r->d_total_rays)) != IZPI_OK) return rc;
+  IZ_CUDA(cudaEventRecord(s.resolved, st));
+  s.busy = false;
+  return IZPI_OK;
+}
+
+int sync_slots(RenderState* r) {
+  for (BatchSlot& s : r->slot) IZ_CUDA(cudaStreamSynchronize(s.stream));
   return IZPI_OK;
 }
 
@@ -678,12 +735,13 @@ int canvas_to_host(izpi_ctx* ctx, RenderState* r, double* host, bool epilogue) {
   cudaStream_t st = ctx->stream;
   long long n_px = (long long)r->rp.width * r->rp.height;
   int rc;
-  if ((rc = launch(ctx, mean_kernel, dim3((unsigned)((n_px + 255) / 256)), dim3(256), 0, r->rp, r->d_canvas, r->d_out, n_px)) != IZPI_OK) return rc;
+  if ((rc = sync_slots(r)) != IZPI_OK) return rc;
+  if ((rc = launch(ctx, st, mean_kernel, dim3((unsigned)((n_px + 255) / 256)), dim3(256), 0, r->rp, r->d_canvas, r->d_out, n_px)) != IZPI_OK) return rc;
   if (epilogue && r->rp.sampler == IZPI_SAMPLER_SPECTRAL) {  // renderer.go:216-219
     IZ_CUDA(cudaMemcpyAsync(r->d_snap, r->d_out, (size_t)n_px * 32, cudaMemcpyDeviceToDevice, st));
     dim3 b(32, 8), g((r->rp.width + 31) / 32, (r->rp.height + 7) / 8);
-    if ((rc = launch(ctx, firefly_kernel, g, b, 0, r->d_snap, r->d_out, r->rp.width, r->rp.height)) != IZPI_OK) return rc;
-    if ((rc = launch(ctx, xyz_to_acescg_kernel, dim3((unsigned)((n_px + 255) / 256)), dim3(256), 0, r->d_out, n_px,
+    if ((rc = launch(ctx, st, firefly_kernel, g, b, 0, r->d_snap, r->d_out, r->rp.width, r->rp.height)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, st, xyz_to_acescg_kernel, dim3((unsigned)((n_px + 255) / 256)), dim3(256), 0, r->d_out, n_px,
                      ctx->scene.camera.exposure)) != IZPI_OK) return rc;
   }
   IZ_CUDA(cudaMemcpyAsync(host, r->d_out, (size_t)n_px * 32, cudaMemcpyDeviceToHost, st));
@@ -715,9 +773,13 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
   // the big buffers (path states, queues, canvas) are allocated once per context and reused by later
   // setups: a render call then costs no cudaMalloc / cudaFree
   RenderState* r = ctx->render;
-  if (!r) { r = new RenderState(); ctx->render = r; }
+  if (!r) {
+    r = new RenderState();
+    ctx->render = r;
+    const char* e = getenv("IZPI_BATCH_PATHS");
+    if (e) { long v = atol(e); if (v >= 1024 && v <= (1l << 28)) r->batch_paths = (int32_t)v; }
+  }
   r->cfg = *cfg;
-  r->total_rays = 0;
   RenderParams& rp = r->rp;
   rp.width = cfg->width; rp.height = cfg->height; rp.spp = cfg->spp; rp.max_depth = cfg->max_depth; rp.sampler = cfg->sampler;
   for (int k = 0; k < 3; k++) rp.background[k] = cfg->background[k];
@@ -738,20 +800,28 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
     IZ_CUDA(cudaMalloc(&r->d_snap, n_px * 32));
     r->canvas_capacity = n_px;
   }
-  IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px * 32, ctx->stream));
-  if (!r->d_paths) {
+  if (!r->allocated) {
+    IZ_CUDA(cudaMalloc(&r->d_total_rays, sizeof(unsigned long long)));
     int32_t cap = r->batch_paths;
-    IZ_CUDA(cudaMalloc(&r->d_paths, (size_t)cap * sizeof(PathState)));
-    IZ_CUDA(cudaMalloc(&r->q.cur, (size_t)cap * 4));
-    IZ_CUDA(cudaMalloc(&r->q.next, (size_t)cap * 4));
-    IZ_CUDA(cudaMalloc(&r->q.bins, (size_t)cap * 4 * kClasses));
-    IZ_CUDA(cudaMalloc(&r->q.counters, 16 * sizeof(unsigned long long)));
-    r->q.capacity = cap;
-    IZ_CUDA(cudaHostAlloc(&r->h_count, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
-    IZ_CUDA(cudaHostGetDevicePointer(&r->d_count_mapped, r->h_count, 0));
-    IZ_CUDA(cudaEventCreateWithFlags(&r->ev[0], cudaEventDisableTiming));
-    IZ_CUDA(cudaEventCreateWithFlags(&r->ev[1], cudaEventDisableTiming));
+    for (BatchSlot& s : r->slot) {
+      IZ_CUDA(cudaMalloc(&s.d_paths, (size_t)cap * sizeof(PathState)));
+      IZ_CUDA(cudaMalloc(&s.q.cur, (size_t)cap * 4));
+      IZ_CUDA(cudaMalloc(&s.q.next, (size_t)cap * 4));
+      IZ_CUDA(cudaMalloc(&s.q.bins, (size_t)cap * 4 * kClasses));
+      IZ_CUDA(cudaMalloc(&s.q.counters, 16 * sizeof(unsigned long long)));
+      s.q.capacity = cap;
+      IZ_CUDA(cudaHostAlloc(&s.h_count, 8 * sizeof(unsigned long long), cudaHostAllocMapped));
+      IZ_CUDA(cudaHostGetDevicePointer(&s.d_count_mapped, s.h_count, 0));
+      IZ_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      for (cudaEvent_t& e : s.ev) IZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      IZ_CUDA(cudaEventCreateWithFlags(&s.resolved, cudaEventDisableTiming));
+    }
+    r->allocated = true;
   }
+  rc = sync_slots(r);
+  if (rc != IZPI_OK) return rc;
+  IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px * 32, ctx->stream));
+  IZ_CUDA(cudaMemsetAsync(r->d_total_rays, 0, sizeof(unsigned long long), ctx->stream));
   IZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return IZPI_OK;
 }
@@ -772,28 +842,48 @@ int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* tiles, dou
     for (uint32_t y = y0; y <= y1; y++)
       for (uint32_t x = x0; x <= x1; x++) px.push_back(x | (y << 16));
   }
-  if ((int64_t)px.size() > r->pixel_capacity) {
-    cudaFree(r->d_pixels);
-    r->d_pixels = nullptr; r->pixel_capacity = 0;
-    IZ_CUDA(cudaMalloc(&r->d_pixels, px.size() * 4));
-    r->pixel_capacity = (int64_t)px.size();
-  }
   const int s_total = r->cfg.sample_count, s_off = r->cfg.sample_offset;
   if (!px.empty() && s_total > 0) {
     // batches: as many samples per pixel as fit, then as many pixels as fit; sample blocks in
     // increasing order so that every pixel's running sum adds its samples in the reference's order
-    const int64_t cap = r->q.capacity;
+    struct Batch { int64_t p0; int np, s0, sc; };
+    std::vector<Batch> batches;
+    const int64_t cap = r->slot[0].q.capacity;
     int s_block = (int)std::min<int64_t>(s_total, cap);
     int64_t px_block = std::max<int64_t>(1, cap / s_block);
+    // keep both slots busy even when everything would fit one batch
+    if ((int64_t)px.size() <= px_block && s_block == s_total && (int64_t)px.size() * s_total > (1 << 20))
+      px_block = ((int64_t)px.size() + 1) / 2;
     for (int64_t p0 = 0; p0 < (int64_t)px.size(); p0 += px_block) {
       int np = (int)std::min<int64_t>(px_block, (int64_t)px.size() - p0);
-      IZ_CUDA(cudaMemcpyAsync(r->d_pixels, px.data() + p0, (size_t)np * 4, cudaMemcpyHostToDevice, ctx->stream));
-      for (int s0 = 0; s0 < s_total; s0 += s_block) {
-        int sc = std::min(s_block, s_total - s0);
-        int rc = render_batch(ctx, r, np, s_off + s0, sc);
-        if (rc != IZPI_OK) return rc;
-      }
+      for (int s0 = 0; s0 < s_total; s0 += s_block) batches.push_back({p0, np, s_off + s0, std::min(s_block, s_total - s0)});
     }
+    LaunchCfg lc;
+    int rc = launch_cfg(ctx, lc);
+    if (rc != IZPI_OK) return rc;
+    size_t next = 0;
+    int resolved_upto = 0;          // batches [0, resolved_upto) have their resolve enqueued
+    cudaEvent_t last_resolved = nullptr;
+    for (;;) {
+      bool any = false;
+      for (BatchSlot& s : r->slot) {
+        if (!s.busy && next < batches.size()) {
+          const Batch& b = batches[next];
+          if ((rc = batch_start(ctx, r, s, (int)next, px.data() + b.p0, b.np, b.s0, b.sc)) != IZPI_OK) return rc;
+          next++;
+        }
+        if (!s.busy) continue;
+        any = true;
+        if (!s.drained && (rc = batch_step(ctx, r, s, lc)) != IZPI_OK) return rc;
+        if (s.drained && s.batch == resolved_upto) {  // resolves strictly in batch order
+          if ((rc = batch_finish(ctx, r, s, last_resolved)) != IZPI_OK) return rc;
+          last_resolved = s.resolved;
+          resolved_upto++;
+        }
+      }
+      if (!any && next >= batches.size()) break;
+    }
+    if ((rc = sync_slots(r)) != IZPI_OK) return rc;
   }
   if (canvas_rgba) return canvas_to_host(ctx, r, canvas_rgba, false);
   return IZPI_OK;
@@ -802,6 +892,8 @@ int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* tiles, dou
 int izpi_render_canvas_device(izpi_ctx* ctx, double** d_canvas) {
   if (!ctx || !d_canvas) { set_error("izpi_render_canvas_device: bad argument"); return IZPI_EINVAL; }
   if (!ctx->render) { set_error("izpi_render_canvas_device: izpi_render_setup has not been called"); return IZPI_ESTATE; }
+  int rc = sync_slots(ctx->render);
+  if (rc != IZPI_OK) return rc;
   IZ_CUDA(cudaStreamSynchronize(ctx->stream));
   *d_canvas = ctx->render->d_canvas;
   return IZPI_OK;
@@ -812,7 +904,13 @@ int izpi_render_finish(izpi_ctx* ctx, double* canvas_rgba, uint64_t* total_rays)
   RenderState* r = ctx->render;
   if (!r) { set_error("izpi_render_finish: izpi_render_setup has not been called"); return IZPI_ESTATE; }
   IZ_CUDA(cudaSetDevice(ctx->device));
-  if (total_rays) *total_rays = r->total_rays;
+  if (total_rays) {
+    int rc = sync_slots(r);
+    if (rc != IZPI_OK) return rc;
+    unsigned long long v = 0;
+    IZ_CUDA(cudaMemcpy(&v, r->d_total_rays, sizeof(v), cudaMemcpyDeviceToHost));
+    *total_rays = v;
+  }
   if (canvas_rgba) return canvas_to_host(ctx, r, canvas_rgba, true);
   return IZPI_OK;
 }
