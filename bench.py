@@ -89,17 +89,23 @@ def cpu_baseline(sc, lo, hi, n_sample, threads):
     return n_sample / dt / 1e6, st, (ids, t, org, d)
 
 
-def bench_render(ctx, cuda, scenes, world, rank, barrier):
+def bench_render(ctx, cuda, scenes, world, rank, barrier, with_4k=True):
     """Second half of BASELINE's metric: Msamples/s of the tile renderer, end to end through
     render.New(...).Render() (setup, tiles, NCCL reduce of the fp64 canvas for N>1, epilogue, D2H).
     Strong scaling: the image is fixed, its tiles are dealt to the ranks."""
     import time as _t
     from izpi_b200 import render
     out = []
-    for name, spec, w, h, spp, sampler in (
-            ("config 1: cornell box 400x400, 64 spp, colour", scenes.cornell_box(1.0), 400, 400, 64, cuda.SAMPLER_COLOUR),
-            ("config 4 scene: spectral glass pyramid 1024x1024 at 16 spp (BASELINE: 1024 spp)", scenes.spectral_pyramid(1.0), 1024, 1024, 16, cuda.SAMPLER_SPECTRAL)):
-        ctx.upload(cuda.HostScene(spec))
+    cases = [("config 1: cornell box 400x400, 64 spp, colour", lambda: scenes.cornell_box(1.0), 400, 400, 64, cuda.SAMPLER_COLOUR),
+             ("config 4 scene: spectral glass pyramid 1024x1024 at 16 spp (BASELINE: 1024 spp)", lambda: scenes.spectral_pyramid(1.0), 1024, 1024,
+              16, cuda.SAMPLER_SPECTRAL)]
+    if with_4k:  # the multi-GPU target of BASELINE: a 4K render, tile-sharded
+        cases.append(("config 5 scene: 4K IBL + ~10M-triangle mesh 3840x2160 at 16 spp (BASELINE: 1024 spp)",
+                      lambda: scenes.ibl_displaced_mesh(3840 / 2160), 3840, 2160, 16, cuda.SAMPLER_COLOUR))
+    for name, make, w, h, spp, sampler in cases:
+        spec = make()
+        ctx.upload(cuda.HostScene(spec, threads=max(1, (os.cpu_count() or 8) // world)))
+        del spec
         r = render.New(ctx, w, h, spp, 50, sampler_type=sampler, seed=3)
         render.New(ctx, w, h, 1, 50, sampler_type=sampler, seed=3).Render()  # warm-up
         barrier()
@@ -149,6 +155,7 @@ def main():
     ap.add_argument("--impl", default="izpi_b200")
     ap.add_argument("--rays", type=int, default=N_RAYS, help="rays per step per GPU (default = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-4k", action="store_true", help="skip the 4K / 10M-triangle render (saves ~20 s of host-side scene building)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -235,7 +242,7 @@ def main():
     # results of the two paths agree
     assert np.array_equal(np_ids, d_ids.cpu().numpy()) and np.array_equal(np_t, d_t.cpu().numpy())
 
-    render_info = bench_render(ctx, cuda, scenes, world, rank, barrier)
+    render_info = bench_render(ctx, cuda, scenes, world, rank, barrier, with_4k=not args.no_4k)
     ctx.upload(hs)  # back to the closest-hit scene for the CPU-baseline parity check below
 
     if world > 1:

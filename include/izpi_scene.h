@@ -72,12 +72,13 @@ typedef struct izpi_texture_spec {
 
 enum {
   IZPI_SPEC_GAUSSIAN = 0,  /* texture/spectral_constant.go:26 NewSpectralConstant(peak, centre, width) */
-  IZPI_SPEC_TABULATED = 1  /* spectral_constant.go:37 NewSpectralConstantFromSPD / :47 NewSpectralNeutral */
+  IZPI_SPEC_TABULATED = 1, /* spectral_constant.go:37 NewSpectralConstantFromSPD / :47 NewSpectralNeutral */
+  IZPI_SPEC_IMAGE = 2      /* spectral_image.go:61 NewSpectralImageFromImage: RGB image -> 75 spectral buckets */
 };
 
 typedef struct izpi_spectral_texture_spec {
   int32_t type;
-  int32_t n;                  /* TABULATED: number of samples */
+  int32_t n;                  /* TABULATED: number of samples; IMAGE: index of the RGB image texture */
   double peak, centre, width; /* GAUSSIAN */
   const double* wavelengths;  /* TABULATED [n] */
   const double* values;       /* TABULATED [n] */

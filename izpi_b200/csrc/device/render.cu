@@ -402,7 +402,7 @@ shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* path
         Onb uvw = onb_from_w(h.n);
         (void)onb_local(uvw, random_cosine_direction(rng));  // scatterCommon's ray: two draws, result unused
         s.pdf_w = uvw.w; s.ok = true; s.specular = false;
-        if (spectral) s.atten = mk(m.spectral_tex >= 0 ? spectral_value(sc, m.spectral_tex, p.lambda) : 0.0, 0, 0);
+        if (spectral) s.atten = mk(m.spectral_tex >= 0 ? spectral_value(sc, m.spectral_tex, p.lambda, h.u, h.v) : 0.0, 0, 0);
         else s.atten = m.tex >= 0 ? texture_value(sc, m.tex, h.u, h.v) : mk(0, 0, 0);
       } else if (CLS == IZPI_MAT_METAL) {  // metal.go:34-41; spectral: non_spectral.go:18-20 -> no scatter
         if (!spectral) {
@@ -412,7 +412,7 @@ shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* path
           s.ok = true; s.specular = true;
         }
       } else if (CLS == IZPI_MAT_DIELECTRIC) {  // dielectric.go:156-207
-        double ref_idx = spectral ? spectral_value(sc, m.spectral_tex, p.lambda) : m.s;
+        double ref_idx = spectral ? spectral_value(sc, m.spectral_tex, p.lambda, h.u, h.v) : m.s;
         bool is_reflected;
         s.spec_dir = dielectric_common(r, h, rng, ref_idx, is_reflected);
         s.ok = true; s.specular = true;
@@ -420,7 +420,7 @@ shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* path
           double albedo = 1.0;
           if (!is_reflected) {
             double pl = path_length(sc, h.p, s.spec_dir, r.time, p.lambda);
-            if (m.spectral_absorption_tex >= 0) albedo = exp(-spectral_value(sc, m.spectral_absorption_tex, p.lambda) * pl);
+            if (m.spectral_absorption_tex >= 0) albedo = exp(-spectral_value(sc, m.spectral_absorption_tex, p.lambda, h.u, h.v) * pl);
           }
           s.atten = mk(albedo, 0, 0);
         } else if (m.compute_beer_lambert && !(m.v[0] == 0 && m.v[1] == 0 && m.v[2] == 0) && !is_reflected) {
@@ -431,13 +431,13 @@ shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* path
         }
       } else if (CLS == IZPI_MAT_DIFFUSE_LIGHT) {  // diffuselight.go:41-63
         if (dot(h.n, r.d) < 0.0) {
-          if (spectral) emitted = mk(m.spectral_tex >= 0 ? spectral_value(sc, m.spectral_tex, p.lambda) : 0.0, 0, 0);
+          if (spectral) emitted = mk(m.spectral_tex >= 0 ? spectral_value(sc, m.spectral_tex, p.lambda, h.u, h.v) : 0.0, 0, 0);
           else emitted = m.tex >= 0 ? texture_value(sc, m.tex, h.u, h.v) : mk(0, 0, 0);
         }
       } else {  // PBR
         if (spectral) {
           double albedo;
-          if (m.spectral_tex >= 0) albedo = spectral_value(sc, m.spectral_tex, p.lambda);
+          if (m.spectral_tex >= 0) albedo = spectral_value(sc, m.spectral_tex, p.lambda, h.u, h.v);
           else { d3 rgb = texture_value(sc, m.tex, h.u, h.v); albedo = 0.299 * rgb.x + 0.587 * rgb.y + 0.114 * rgb.z; }
           pbr_common(sc, m, r, h, rng, s);
           s.atten = mk(s.specular ? albedo * 1.5 : albedo, 0, 0);

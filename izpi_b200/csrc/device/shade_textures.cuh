@@ -43,8 +43,35 @@ __device__ __forceinline__ double spd_interp(const double* w, const double* val,
   return 0.0;
 }
 
-__device__ __forceinline__ double spectral_value(const DScene& sc, int tex, double lambda) {
+// SpectralImage.rgbToSpectralValue (texture/spectral_image.go:136-190).  The reference tabulates it per pixel
+// and per 5-nm bucket at load time; it is a pure function of the texel's RGB and the bucket wavelength, so
+// the device evaluates it on the fly instead of keeping 75 planes per image in HBM.
+__device__ __forceinline__ double rgb_to_spectral_value(double r, double g, double b, double wl) {
+  double sv = 0.0;
+  const double two_w2 = 2.0 * 60.0 * 60.0;
+  if (wl >= 580.0 && wl <= 750.0) { double d = fabs(wl - 650.0); sv += r * exp(-(d * d) / two_w2); }
+  if (wl >= 480.0 && wl <= 620.0) { double d = fabs(wl - 550.0); sv += g * exp(-(d * d) / two_w2); }
+  if (wl >= 380.0 && wl <= 520.0) { double d = fabs(wl - 450.0); sv += b * exp(-(d * d) / two_w2); }
+  double mx = r > (g > b ? g : b) ? r : (g > b ? g : b);  // math.Max(r, math.Max(g, b))
+  if (fabs(r - g) < 0.15 && fabs(g - b) < 0.15 && fabs(r - b) < 0.15) sv = sv > mx ? sv : mx;
+  if (mx > 0.7 && sv < mx * 0.8) sv = sv > mx * 0.8 ? sv : mx * 0.8;
+  double c = 1.0 < sv ? 1.0 : sv;
+  return 0.0 > c ? 0.0 : c;
+}
+
+__device__ __forceinline__ double spectral_value(const DScene& sc, int tex, double lambda, double u, double v) {
   const DSpectralTexture& t = sc.spectex[tex];
+  if (t.type == IZPI_SPEC_IMAGE) {  // SpectralImage.Value (spectral_image.go:193-245): nearest texel, bucket at or above lambda
+    d3 rgb = texture_value(sc, t.n, u, v);
+    int idx = 74;
+    if (lambda < 380.0) idx = 0;
+    else if (lambda > 750.0) idx = 74;
+    else {
+      for (int i = 0; i < 75; i++)
+        if (lambda <= 380.0 + 5.0 * (double)i) { idx = i; break; }
+    }
+    return rgb_to_spectral_value(rgb.x, rgb.y, rgb.z, 380.0 + 5.0 * (double)idx);
+  }
   if (t.type == IZPI_SPEC_TABULATED) return spd_interp(t.wavelengths, t.values, t.n, lambda);
   double e = (lambda - t.centre) / t.width;
   return t.peak * exp(-(e * e));  // math.Pow(x, 2) is exactly x*x

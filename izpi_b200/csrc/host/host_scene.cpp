@@ -201,11 +201,15 @@ int izpi_host_scene_create(const izpi_scene_spec* spec, int threads, izpi_host_s
   s->materials.assign(spec->materials, spec->materials + spec->n_materials);
   s->textures.assign(spec->textures, spec->textures + spec->n_textures);  // image pixels stay borrowed until upload
   s->spectex.assign(spec->spectral_textures, spec->spectral_textures + spec->n_spectral_textures);
-  for (auto& t : s->spectex)
+  for (auto& t : s->spectex) {
+    if (t.type == IZPI_SPEC_IMAGE && (t.n < 0 || t.n >= spec->n_textures || spec->textures[t.n].type != IZPI_TEX_IMAGE)) {
+      delete s; set_error("spectral image texture refers to a missing image texture"); return IZPI_EINVAL;
+    }
     if (t.type == IZPI_SPEC_TABULATED) {
       s->owned.emplace_back(t.wavelengths, t.wavelengths + t.n); t.wavelengths = s->owned.back().data();
       s->owned.emplace_back(t.values, t.values + t.n); t.values = s->owned.back().data();
     }
+  }
 
   {  // camera.New (camera/camera.go:28-58)
     const izpi_camera_spec& c = spec->camera;

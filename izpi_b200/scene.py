@@ -15,7 +15,7 @@ import numpy as np
 PRIM_TRIANGLE, PRIM_SPHERE, PRIM_XYRECT, PRIM_XZRECT, PRIM_YZRECT, PRIM_BOX = range(6)
 WRAP_FLIP, WRAP_ROTATE_Y, WRAP_TRANSLATE = 1, 2, 4
 TEX_CONSTANT, TEX_IMAGE = 0, 1
-SPEC_GAUSSIAN, SPEC_TABULATED = 0, 1
+SPEC_GAUSSIAN, SPEC_TABULATED, SPEC_IMAGE = 0, 1, 2
 MAT_LAMBERT, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_PBR = range(5)
 WORLD_SLICE, WORLD_BVH4 = 0, 1
 
@@ -110,6 +110,11 @@ class SceneSpec:
         self.spectral_textures.append(SpectralTextureSpec(type=SPEC_TABULATED, n=len(w), wavelengths=w.ctypes.data, values=v.ctypes.data))
         return len(self.spectral_textures) - 1
 
+    def spectral_image(self, image_tex: int) -> int:  # texture.NewSpectralImageFromImage over an image texture
+        assert self.textures[image_tex].type == TEX_IMAGE
+        self.spectral_textures.append(SpectralTextureSpec(type=SPEC_IMAGE, n=image_tex))
+        return len(self.spectral_textures) - 1
+
     def spectral_neutral(self, reflectance) -> int:  # texture.NewSpectralNeutral (spectral_constant.go:47-62)
         w = np.arange(380.0, 751.0, 10.0)
         return self.spectral_tabulated(w, np.full_like(w, float(reflectance)))
@@ -151,8 +156,10 @@ class SceneSpec:
     def spectral_diffuse_light(self, spectral_tex) -> int:  # material.NewSpectralDiffuseLight
         return self._mat(type=MAT_DIFFUSE_LIGHT, spectral_tex=spectral_tex)
 
-    def pbr(self, albedo, normal=-1, roughness=-1, metalness=-1) -> int:  # material.NewPBR
-        return self._mat(type=MAT_PBR, tex=albedo, normal_tex=normal, roughness_tex=roughness, metalness_tex=metalness)
+    def pbr(self, albedo, normal=-1, roughness=-1, metalness=-1, spectral_albedo=-1) -> int:
+        # material.NewPBR / NewPBRWithSpectralAlbedo (transport.go:209-250: spectral scenes wrap the albedo image)
+        return self._mat(type=MAT_PBR, tex=albedo, normal_tex=normal, roughness_tex=roughness, metalness_tex=metalness,
+                         spectral_tex=spectral_albedo)
 
     # ---- primitives ---------------------------------------------------------------------
     def _new(self, n) -> np.ndarray:

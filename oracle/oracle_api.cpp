@@ -107,6 +107,7 @@ oracle_scene* oracle_scene_create(const izpi_scene_spec* spec) {
     const izpi_spectral_texture_spec& t = spec->spectral_textures[i];
     SpectralTexture& o = s->spectex[i];
     o.type = t.type; o.peak = t.peak; o.centre = t.centre; o.width = t.width;
+    if (t.type == IZPI_SPEC_IMAGE) o.image = (t.n >= 0 && t.n < (int)s->textures.size()) ? &s->textures[t.n] : nullptr;
     if (t.type == IZPI_SPEC_TABULATED) {
       o.spd.wavelengths.assign(t.wavelengths, t.wavelengths + t.n);
       o.spd.values.assign(t.values, t.values + t.n);

@@ -92,7 +92,39 @@ struct SpectralTexture {  // texture/spectral_constant.go
   int type = IZPI_SPEC_GAUSSIAN;
   double peak = 0, centre = 0, width = 1;
   SPD spd;
-  double Value(double lambda) const {  // spectral_constant.go:65-74
+  const Texture* image = nullptr;  // IZPI_SPEC_IMAGE: texture.SpectralImage over this RGB image
+  // SpectralImage.rgbToSpectralValue (spectral_image.go:136-190)
+  static double rgbToSpectralValue(double r, double g, double b, double wavelength) {
+    double spectralValue = 0;
+    if (wavelength >= 580.0 && wavelength <= 750.0) {
+      double distance = std::fabs(wavelength - 650.0), width = 60.0;
+      spectralValue += r * std::exp(-(distance * distance) / (2.0 * width * width));
+    }
+    if (wavelength >= 480.0 && wavelength <= 620.0) {
+      double distance = std::fabs(wavelength - 550.0), width = 60.0;
+      spectralValue += g * std::exp(-(distance * distance) / (2.0 * width * width));
+    }
+    if (wavelength >= 380.0 && wavelength <= 520.0) {
+      double distance = std::fabs(wavelength - 450.0), width = 60.0;
+      spectralValue += b * std::exp(-(distance * distance) / (2.0 * width * width));
+    }
+    if (std::fabs(r - g) < 0.15 && std::fabs(g - b) < 0.15 && std::fabs(r - b) < 0.15) {
+      double maxRGB = gomax(r, gomax(g, b));
+      spectralValue = gomax(spectralValue, maxRGB);
+    }
+    double maxRGB = gomax(r, gomax(g, b));
+    if (maxRGB > 0.7 && spectralValue < maxRGB * 0.8) spectralValue = gomax(spectralValue, maxRGB * 0.8);
+    return gomax(0.0, gomin(1.0, spectralValue));
+  }
+  double Value(double lambda, double u = 0, double v = 0) const {  // spectral_constant.go:65-74
+    if (type == IZPI_SPEC_IMAGE) {  // SpectralImage.Value / findWavelengthIndex (spectral_image.go:193-245)
+      Vec3 rgb = image->Value(u, v);
+      int idx = 74;
+      if (lambda < 380.0) idx = 0;
+      else if (lambda > 750.0) idx = 74;
+      else for (int i = 0; i < 75; i++) if (lambda <= 380.0 + 5.0 * i) { idx = i; break; }
+      return rgbToSpectralValue(rgb.X, rgb.Y, rgb.Z, 380.0 + 5.0 * idx);
+    }
     if (type == IZPI_SPEC_TABULATED) return interpolateSPD(lambda);
     double exponent = -std::pow((lambda - centre) / width, 2);
     return peak * std::exp(exponent);
@@ -292,16 +324,16 @@ struct Material {
     switch (type) {
       case IZPI_MAT_LAMBERT:  // lambertian.go:63-71
         lambertCommon(hr, rng, s);
-        s.spectralAtten = spectral->Value(lambda);
+        s.spectralAtten = spectral->Value(lambda, hr.u, hr.v);
         return true;
       case IZPI_MAT_DIELECTRIC: {  // dielectric.go:184-207
-        double refIdx = spectral->Value(lambda);
+        double refIdx = spectral->Value(lambda, hr.u, hr.v);
         bool isReflected;
         Ray scattered = dielectricCommon(r, hr, rng, refIdx, isReflected);
         double albedo;
         if (!isReflected) {
           double pathLength = calculatePathLength(r, hr, scattered);
-          albedo = spectralAbsorption ? std::exp(-spectralAbsorption->Value(lambda) * pathLength) : 1.0;  // :106-114
+          albedo = spectralAbsorption ? std::exp(-spectralAbsorption->Value(lambda, hr.u, hr.v) * pathLength) : 1.0;  // :106-114
         } else {
           albedo = 1.0;
         }
@@ -320,7 +352,7 @@ struct Material {
   }
 
   double SpectralAlbedo(double u, double vv, double lambda) const {  // pbr.go:285-293
-    if (spectral) return spectral->Value(lambda);
+    if (spectral) return spectral->Value(lambda, u, vv);
     Vec3 rgb = tex->Value(u, vv);
     return 0.299 * rgb.X + 0.587 * rgb.Y + 0.114 * rgb.Z;
   }
@@ -339,7 +371,7 @@ struct Material {
     return Vec3();
   }
   double EmittedSpectral(const Ray& rIn, const HitRecord& rec, double lambda) const {  // diffuselight.go:58-63
-    if (type == IZPI_MAT_DIFFUSE_LIGHT && Dot(rec.normal, rIn.direction) < 0.0) return spectral->Value(lambda);
+    if (type == IZPI_MAT_DIFFUSE_LIGHT && Dot(rec.normal, rIn.direction) < 0.0) return spectral->Value(lambda, rec.u, rec.v);
     return 0.0;
   }
 };

@@ -140,3 +140,15 @@ def test_ibl_metal_mesh_same_path(ctx, oracle_mod):
     Metal mesh, glass sphere; all specular, as in scenes.Environment."""
     sc = scenes.ibl_displaced_mesh(16 / 9, 120, 60, (256, 128))
     _same_path(ctx, oracle_mod, sc, 64, 36, 8, cuda.SAMPLER_COLOUR, min_close=0.97)
+
+
+def test_spectral_pbr_image_albedo_same_path(ctx, oracle_mod):
+    """Spectral PBR (pbr.go:158-263) with a SpectralImage albedo (spectral_image.go:61-245), the material
+    transport builds for PBR in SPECTRAL scenes (transport.go:209-250)."""
+    sc = scenes.spectral_pyramid(1.0)
+    alb, rough, metal, nrm = scenes.pbr_textures(64)
+    a = sc.image_texture(alb)
+    pbr = sc.pbr(a, sc.image_texture(nrm), sc.image_texture(rough), sc.image_texture(metal), spectral_albedo=sc.spectral_image(a))
+    tv, tuv = scenes.torus_mesh(60, 40, centre=(50.0, 60.0, 50.0), major=30.0, minor=12.0, amp=3.0, scale=0.5)
+    sc.triangles(tv, pbr, tuv)
+    _same_path(ctx, oracle_mod, sc, 40, 40, 16, cuda.SAMPLER_SPECTRAL, min_close=0.93)
