@@ -56,6 +56,24 @@ class _DevicePtr:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+_pinned = {}
+
+
+def host_canvas(height: int, width: int) -> np.ndarray:
+    """The float64 RGBA canvas (floatimage.Float64NRGBA.Pix) in page-locked host memory, so that the one
+    device-to-host copy of a frame (265 MB at 4K) runs at PCIe speed.  Falls back to pageable memory
+    when torch is absent."""
+    try:
+        import torch
+        key = (height, width)
+        if key not in _pinned:
+            _pinned.clear()
+            _pinned[key] = torch.empty((height, width, 4), dtype=torch.float64, pin_memory=torch.cuda.is_available())
+        return _pinned[key].numpy()
+    except ImportError:
+        return np.empty((height, width, 4), dtype=np.float64)
+
+
 class Renderer:
     """render.RendererImpl (renderer.go:26-44)."""
 
@@ -105,10 +123,10 @@ class Renderer:
             if rank != 0:
                 return None
             self.num_rays = int(t.item())
-            canvas = np.zeros((self.size_y, self.size_x, 4), dtype=np.float64)
+            canvas = host_canvas(self.size_y, self.size_x)
             cuda.check(L.izpi_render_finish(h, canvas.ctypes.data, None))
             return canvas
-        canvas = np.zeros((self.size_y, self.size_x, 4), dtype=np.float64)
+        canvas = host_canvas(self.size_y, self.size_x)
         cuda.check(L.izpi_render_finish(h, canvas.ctypes.data, C.byref(rays)))
         self.num_rays = rays.value
         return canvas
