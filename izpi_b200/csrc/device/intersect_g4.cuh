@@ -26,12 +26,15 @@
 namespace izpi {
 
 constexpr int kG4Stack = 64;        // entries per ray (bvh4.go:71)
+constexpr int kG4Slab = kG4Stack + 7;  // int2 slots of shared memory per ray: the stack, the fp64 ray (6 doubles), 1 pad
 constexpr int kNodeStragglers = 4;  // default: leave the node phase when <= this many groups are still in it
 
+// Per-lane registers hold only what the node phase needs; the fp64 origin/direction (used by the primitive
+// tests alone) live in the ray's shared-memory slab behind its stack, which buys resident warps: the kernel is
+// latency-bound and its throughput is linear in them (scripts/sweep_blocks.sh).
 struct G4State {
-  DRay r;
   float ox, oy, oz, ix, iy, iz;
-  double tmin, tmax;
+  double tmax;
   int best;   // record index of the closest primitive so far
   int sp;     // stack pointer
   int cur;    // >= 0: inner node to visit; kLeaf: leaf pending; kIdle: no ray
@@ -41,11 +44,14 @@ struct G4State {
 constexpr int kLeaf = -2, kIdle = -1;
 
 // stack entry: ref >= 0 inner node; ref < 0 leaf: ~ref = (first primitive << 2) | (count - 1)
-__device__ __forceinline__ void g4_begin(G4State& s, const DScene& sc, const DRay& r, double tmin, double tmax) {
-  s.r = r;
+__device__ __forceinline__ void g4_begin(G4State& s, const DScene& sc, const DRay& r, double tmax, int2* slab, int j) {
+  if (j == 0) {
+    double* rs = reinterpret_cast<double*>(slab + kG4Stack);
+    rs[0] = r.o.x; rs[1] = r.o.y; rs[2] = r.o.z; rs[3] = r.d.x; rs[4] = r.d.y; rs[5] = r.d.z;
+  }
   s.ix = (float)(1.0 / r.d.x); s.iy = (float)(1.0 / r.d.y); s.iz = (float)(1.0 / r.d.z);  // bvh4.go:61-66
   s.ox = (float)r.o.x; s.oy = (float)r.o.y; s.oz = (float)r.o.z;                            // bvh4.go:67
-  s.tmin = tmin; s.tmax = tmax; s.best = -1; s.sp = 0;
+  s.tmax = tmax; s.best = -1; s.sp = 0;
   s.cur = sc.n_nodes > 0 ? 0 : kIdle;
   s.leaf = 0;
   // (bound - o) * inv is NaN only for 0 * Inf or Inf * 0: impossible when the origin is small enough for the
@@ -131,7 +137,7 @@ __device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2
 // `if hit { tMax = rec.T() }` loop (bvh4.go:125-134) over the four candidates.
 template <bool COUNT>
 __device__ __forceinline__ void g4_leaf_phase(G4State& s, const DScene& sc, const int2* stack, unsigned lane, int gshift, int j,
-                                              uint32_t& n_nodes, uint32_t& n_prims) {
+                                              uint32_t& n_nodes, uint32_t& n_prims, double tmin) {
   const unsigned full = 0xffffffffu;
   const bool in_leaf = s.cur == kLeaf;
   if (!__any_sync(full, in_leaf)) return;
@@ -140,8 +146,11 @@ __device__ __forceinline__ void g4_leaf_phase(G4State& s, const DScene& sc, cons
   double t = 0;
   if (in_leaf && j < cnt) {
     PrimRec pr = load_rec(sc.prims + start + j);
+    const double* rs = reinterpret_cast<const double*>(stack + kG4Stack);
+    DRay r;
+    r.o = mk(rs[0], rs[1], rs[2]); r.d = mk(rs[3], rs[4], rs[5]); r.time = 0; r.lambda = 0;
     DHit h;
-    ok = prim_hit<false>(sc, start + j, pr, s.r, s.tmin, s.tmax, h);
+    ok = prim_hit<false>(sc, start + j, pr, r, tmin, s.tmax, h);
     t = h.t;
     strict = tag_type(pr.tag) == IZPI_PRIM_SPHERE;  // Sphere.Hit compares strictly (sphere.go:73,84)
     if (COUNT) n_prims++;

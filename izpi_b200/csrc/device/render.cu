@@ -208,22 +208,22 @@ extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* pat
 // 8 paths per warp, queue indices drawn in chunks, finished groups replaced immediately.
 constexpr int kExtendChunk = 256;
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)  // 80 registers: six resident blocks per SM (latency-bound kernel)
 extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q, int stragglers) {
   extern __shared__ int2 g4_stack_smem[];
   const unsigned full = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const int j = lane & 3, gshift = (lane >> 2) * 4;
-  int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 2) * (kG4Stack + 1);
-  const long long n = (long long)q.counters[0];
+  int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 2) * kG4Slab;
+  const int n = (int)q.counters[0];  // live paths of this bounce (a batch holds < 2^31 paths)
   // queue indices per atomicAdd: large when there is plenty of work, down to one packet of 8 when a late
   // bounce has only a few thousand live paths (otherwise a handful of warps would walk them serially)
-  const long long warps = (long long)gridDim.x * (kThreads / 32);
-  long long chunk = (n / (warps * 4) + 7) & ~7ll;
+  const int warps = (int)gridDim.x * (kThreads / 32);
+  int chunk = (n / (warps * 4) + 7) & ~7;
   chunk = chunk < 8 ? 8 : (chunk > kExtendChunk ? kExtendChunk : chunk);
   uint32_t nn = 0, np = 0;
-  unsigned long long traced = 0;
-  long long chunk_next = 0, chunk_end = 0;
+  unsigned traced = 0;
+  int chunk_next = 0, chunk_end = 0;
   bool exhausted = false;
   G4State s;
   s.cur = kIdle;
@@ -232,12 +232,11 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
     unsigned idle = __ballot_sync(full, s.cur == kIdle);
     if (idle) {
       if (chunk_next >= chunk_end && !exhausted) {
-        long long b = 0;
-        if (lane == 0) b = (long long)atomicAdd(&q.counters[7], (unsigned long long)chunk);
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(&q.counters[7], (unsigned long long)chunk);
         b = __shfl_sync(full, b, 0);
-        chunk_next = b;
-        chunk_end = b + chunk < n ? b + chunk : n;
-        if (b >= n) { exhausted = true; chunk_next = chunk_end = 0; }
+        if (b >= (unsigned long long)n) { exhausted = true; chunk_next = chunk_end = 0; }
+        else { chunk_next = (int)b; chunk_end = (int)b + chunk < n ? (int)b + chunk : n; }
       }
       int before = __popc(idle & ((1u << gshift) - 1u)) >> 2, total = __popc(idle) >> 2;
       if (s.cur == kIdle && chunk_next + before < chunk_end) {
@@ -251,15 +250,15 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
           pi = -1;
         } else {
           if (j == 0) traced++;  // atomic.AddUint64(numRays, 1) (colour.go:38)
-          g4_begin(s, sc, path_ray(p), 0.001, DBL_MAX);
+          g4_begin(s, sc, path_ray(p), DBL_MAX, stack, j);
         }
       }
-      long long take = chunk_end - chunk_next;
+      int take = chunk_end - chunk_next;
       chunk_next += take < total ? take : total;
       if (exhausted && __ballot_sync(full, s.cur == kIdle && pi < 0) == full) break;
     }
     g4_node_phase<false>(s, sc, stack, lane, gshift, j, nn, stragglers);
-    g4_leaf_phase<false>(s, sc, stack, lane, gshift, j, nn, np);
+    g4_leaf_phase<false>(s, sc, stack, lane, gshift, j, nn, np, 0.001);
     const bool done = s.cur == kIdle && pi >= 0;
     if (__any_sync(full, done)) {
       bool hit = false;
@@ -278,7 +277,7 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
       if (done) pi = -1;
     }
   }
-  if (traced) atomicAdd(&q.counters[8], traced);
+  if (traced) atomicAdd(&q.counters[8], (unsigned long long)traced);
 }
 
 // ---- shade ----------------------------------------------------------------------------------
@@ -642,7 +641,7 @@ struct LaunchCfg {
 
 int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
   lc.smem = (size_t)kStackDepth * kThreads * sizeof(int32_t);
-  lc.smem4 = (size_t)(kThreads / 4) * (kG4Stack + 1) * sizeof(int2);
+  lc.smem4 = (size_t)(kThreads / 4) * kG4Slab * sizeof(int2);
   static thread_local int ext_blocks = 0, ext4_blocks = 0;
   if (!ext_blocks) {
     IZ_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));

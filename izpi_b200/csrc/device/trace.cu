@@ -1,6 +1,7 @@
 // trace.cu -- batched closest hit: the hitable.Hitable.Hit seam (internal/hitable/api.go:15) for a
 // whole ray batch.  Persistent warps pull 32-ray packets from a global work queue; each lane walks
 // the BVH4 in the reference's order with its own short stack in shared memory.
+#include <cstdlib>
 #include <cstring>
 
 #include "intersect_g4.cuh"
@@ -51,7 +52,7 @@ trace_kernel(const __grid_constant__ DScene sc, long long n, const double* __res
 // and the warp alternates between a node phase and a leaf phase (intersect_g4.cuh).
 constexpr int kChunk = 256;
 #ifndef IZPI_G4_MIN_BLOCKS
-#define IZPI_G4_MIN_BLOCKS 5
+#define IZPI_G4_MIN_BLOCKS 6
 #endif
 
 template <bool COUNT>
@@ -63,47 +64,49 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
   const unsigned lane = threadIdx.x & 31u;
   const int g = lane >> 2, j = lane & 3;
   const int gshift = g * 4;
-  const unsigned gmask = 0xfu << gshift;
-  int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 2) * (kG4Stack + 1);
-  const long long warps = (long long)gridDim.x * (kTraceThreads / 32);
-  long long chunk = (n / (warps * 4) + 7) & ~7ll;  // rays per atomicAdd: shrinks for small batches (tail balance)
+  int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 2) * kG4Slab;
+  // all ray indices are 32-bit here (the host entry points cut larger batches into launches below 2^31 rays)
+  const int n32 = (int)n;
+  const int warps = (int)gridDim.x * (kTraceThreads / 32);
+  int chunk = (n32 / (warps * 4) + 7) & ~7;  // rays per atomicAdd: shrinks for small batches (tail balance)
   chunk = chunk < 8 ? 8 : (chunk > kChunk ? kChunk : chunk);
   uint32_t n_nodes = 0, n_prims = 0;
-  long long chunk_next = 0, chunk_end = 0;  // warp-uniform
+  int chunk_next = 0, chunk_end = 0;  // warp-uniform
   bool exhausted = false;
   G4State s;
   s.cur = kIdle;
-  long long ray = -1;
+  int ray = -1;
   for (;;) {
     // ---- hand rays to idle groups
     unsigned idle = __ballot_sync(0xffffffffu, s.cur == kIdle);
     if (idle) {
       if (chunk_next >= chunk_end && !exhausted) {
-        long long b = 0;
-        if (lane == 0) b = (long long)atomicAdd(&counters[0], (unsigned long long)chunk);
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(&counters[0], (unsigned long long)chunk);
         b = __shfl_sync(0xffffffffu, b, 0);
-        chunk_next = b;
-        chunk_end = b + chunk < n ? b + chunk : n;
-        if (b >= n) { exhausted = true; chunk_next = chunk_end = 0; }
+        if (b >= (unsigned long long)n32) { exhausted = true; chunk_next = chunk_end = 0; }
+        else { chunk_next = (int)b; chunk_end = (int)b + chunk < n32 ? (int)b + chunk : n32; }
       }
       int before = __popc(idle & ((1u << gshift) - 1u)) >> 2;  // idle groups ahead of mine
       int total = __popc(idle) >> 2;
       if (s.cur == kIdle && chunk_next + before < chunk_end) {
         ray = chunk_next + before;
+        const double* po = org + 3 * (size_t)ray;
+        const double* pd = dir + 3 * (size_t)ray;
         DRay r;
-        r.o = mk(org[3 * ray], org[3 * ray + 1], org[3 * ray + 2]);
-        r.d = mk(dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2]);
+        r.o = mk(po[0], po[1], po[2]);
+        r.d = mk(pd[0], pd[1], pd[2]);
         r.time = 0; r.lambda = 0;
-        g4_begin(s, sc, r, tmin, tmax);
+        g4_begin(s, sc, r, tmax, stack, j);
         if (s.cur == kIdle && j == 0) { ids[ray] = -1; ts[ray] = 0.0; }
       }
-      long long take = chunk_end - chunk_next;
+      int take = chunk_end - chunk_next;
       chunk_next += take < total ? take : total;
       if (exhausted && __ballot_sync(0xffffffffu, s.cur == kIdle) == 0xffffffffu) break;
     }
     // ---- node phase, then leaf phase (both warp-uniform)
     g4_node_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, stragglers);
-    g4_leaf_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, n_prims);
+    g4_leaf_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, n_prims, tmin);
     // ---- finished rays write their answer
     if (s.cur == kIdle && ray >= 0) {
       if (j == 0) {
@@ -135,9 +138,10 @@ __global__ void box4_kernel(int n, const float* __restrict__ org, const float* _
 int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir, double tmin, double tmax,
                  int mode, int32_t* d_ids, double* d_t, cudaStream_t st, bool count, unsigned long long* counters) {
   if (mode != IZPI_TRACE_EXACT) { set_error("izpi_trace_closest: only IZPI_TRACE_EXACT is implemented"); return IZPI_EINVAL; }
+  if (n > (1ll << 30)) { set_error("izpi_trace_closest: at most 2^30 rays per launch; split the batch"); return IZPI_EINVAL; }
   IZ_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), st));
   if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar) {
-    size_t smem4 = (size_t)(kTraceThreads / 4) * (kG4Stack + 1) * sizeof(int2);
+    size_t smem4 = (size_t)(kTraceThreads / 4) * kG4Slab * sizeof(int2);
     auto k4 = count ? trace_g4_kernel<true> : trace_g4_kernel<false>;
     static thread_local int bps4 = 0;
     if (!bps4) {
@@ -145,7 +149,9 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
       if (bps4 < 1) bps4 = 1;
     }
     long long want4 = (n + (kTraceThreads / 4) - 1) / (kTraceThreads / 4);
-    long long grid4 = (long long)ctx->sm_count * bps4;
+    int use_bps = bps4;
+    if (const char* e = getenv("IZPI_TRACE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < use_bps) use_bps = v; }  // occupancy experiments
+    long long grid4 = (long long)ctx->sm_count * use_bps;
     if (grid4 > want4) grid4 = want4;
     if (grid4 < 1) grid4 = 1;
     k4<<<(unsigned)grid4, kTraceThreads, smem4, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, counters,
