@@ -373,3 +373,63 @@ extern "C" int64_t oracle_trace_steps(const oracle_scene* s, int64_t n, const do
   offsets[n] = pos;
   return pos;
 }
+
+// ---- replay of material/dielectric_test.go:47-216 (mockSceneGeometry, LCG(12345), 1000 scatter calls) -------------
+namespace {
+struct MockSceneGeometry : Hitable {  // dielectric_test.go:73-84: always "hits" at (0.5, 0.5, 1.5)
+  bool Hit(const Ray&, double, double, HitRecord& rec, const Material*& mat) const override {
+    rec.t = 2.0; rec.u = 0; rec.v = 0; rec.p = V(0.5, 0.5, 1.5); rec.normal = V(0, 0, 1); mat = nullptr;
+    return true;
+  }
+  bool BoundingBox(AABB&) const override { return false; }
+  bool IsEmitter() const override { return false; }
+};
+}  // namespace
+
+extern "C" {
+// kind 0: TestColoredGlassScattering (RGB, NewColoredDielectric(1.5, (0.1,0.2,0.3)))
+// kind 1: TestSpectralColoredGlassScattering (gaussian refidx (1.5,550,50), gaussian absorption (0.5,480,60), lambda 480)
+// kind 2: TestPathLengthCalculation
+// out: [0] iterations run, [1] found attenuated, [2] found unattenuated, [3..5] first attenuated value(s), [6] path length
+void oracle_probe_dielectric_test(int kind, double* out) {
+  MockSceneGeometry mock;
+  SpectralTexture refidx, absorb;
+  refidx.type = IZPI_SPEC_GAUSSIAN; refidx.peak = 1.5; refidx.centre = 550.0; refidx.width = 50.0;
+  absorb.type = IZPI_SPEC_GAUSSIAN; absorb.peak = 0.5; absorb.centre = 480.0; absorb.width = 60.0;
+  Material m;
+  m.type = IZPI_MAT_DIELECTRIC; m.world = &mock;
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  if (kind == 2) {
+    m.s = 1.5;
+    HitRecord hr; hr.t = 1.0; hr.p = V(0.5, 0.5, 0.5); hr.normal = V(0.577, 0.577, 0.577);
+    Ray r = NewRay(V(0, 0, -2), V(0, 0, 1), 0), scattered = r;
+    out[6] = m.calculatePathLength(r, hr, scattered);
+    return;
+  }
+  if (kind == 0) { m.s = 1.5; m.v = V(0.1, 0.2, 0.3); m.computeBeerLambert = true; }
+  else { m.spectral = &refidx; m.spectralAbsorption = &absorb; }
+  HitRecord hr; hr.t = 1.0; hr.p = V(0, 0, 1); hr.normal = V(0, 0, 1);
+  Ray r = NewRay(V(0, 0, -1), V(0, 0, 1), 0, kind == 1 ? 480.0 : 0.0);
+  Rng rng; rng.mode = 0; rng.state = 12345;  // fastrandom.New(12345, 4294967296, 1664525, 1013904223)
+  bool foundA = false, foundN = false;
+  int it = 0;
+  for (; it < 1000; it++) {
+    ScatterRecord s;
+    if (kind == 0) {
+      m.Scatter(r, hr, rng, s);
+      const double eps = 1e-6;
+      if (s.attenuation.X < 1.0 - eps || s.attenuation.Y < 1.0 - eps || s.attenuation.Z < 1.0 - eps) {
+        if (!foundA) { out[3] = s.attenuation.X; out[4] = s.attenuation.Y; out[5] = s.attenuation.Z; }
+        foundA = true;
+      }
+      if (s.attenuation.X >= 1.0 - eps && s.attenuation.Y >= 1.0 - eps && s.attenuation.Z >= 1.0 - eps) foundN = true;
+    } else {
+      m.SpectralScatter(r, hr, rng, s);
+      if (s.spectralAtten < 1.0) { if (!foundA) out[3] = s.spectralAtten; foundA = true; }
+      if (s.spectralAtten >= 1.0) foundN = true;
+    }
+    if (foundA && foundN) { it++; break; }
+  }
+  out[0] = it; out[1] = foundA; out[2] = foundN;
+}
+}

@@ -247,3 +247,49 @@ def test_sample_wavelength_properties(oracle_mod):
     np.testing.assert_array_equal(xyz, [0.5121, 1.0, 0.0057])
     L.oracle_cie_values(557.5, xyz.ctypes.data)
     np.testing.assert_allclose(xyz, [(0.5121 + 0.5945) / 2, (1.0 + 0.995) / 2, (0.0057 + 0.0039) / 2], rtol=1e-15)
+
+
+def test_dielectric_lcg_replays(oracle_mod):
+    """material/dielectric_test.go:47-216 replayed: mock world, LCG(12345), both reflected (attenuation 1) and
+    transmitted (Beer-Lambert) samples appear within 1000 scatter calls; path length |exit - hit| is in bounds."""
+    import ctypes as C
+    L = oracle_mod.lib()
+    L.oracle_probe_dielectric_test.argtypes = [C.c_int, C.c_void_p]
+    out = np.zeros(8)
+    L.oracle_probe_dielectric_test(2, out.ctypes.data)   # TestPathLengthCalculation
+    assert 0.1 <= out[6] <= 10.0 and out[6] == math.sqrt(0.0 + 0.0 + 1.0)  # |(0.5,0.5,1.5)-(0.5,0.5,0.5)|
+    L.oracle_probe_dielectric_test(0, out.ctypes.data)   # TestColoredGlassScattering
+    assert out[1] == 1 and out[2] == 1 and out[0] <= 1000
+    d = math.sqrt(0.25 + 0.25 + 0.25)                     # hit (0,0,1) -> mock exit (0.5,0.5,1.5)
+    np.testing.assert_allclose(out[3:6], [math.exp(-0.1 * d), math.exp(-0.2 * d), math.exp(-0.3 * d)], rtol=1e-15)
+    L.oracle_probe_dielectric_test(1, out.ctypes.data)   # TestSpectralColoredGlassScattering
+    assert out[1] == 1 and out[2] == 1 and out[0] <= 1000
+    assert out[3] == math.exp(-0.5 * d)                   # gaussian(0.5, 480, 60) at 480 nm is 0.5
+
+
+def test_tbn_normal_map_golden(oracle_mod):
+    """mat3/mat3_test.go:25-30 through Triangle.Hit (triangle.go:250-264): a normal-map texel (0.5, 0.5, 1.0) maps to
+    tangent-space (0,0,1); for the XY-plane triangle with TBN = ((-1,0,0), (0,1,0), (0,0,-1)) the result is (0,0,-1)."""
+    sc = SceneSpec(world_kind=S.WORLD_SLICE)
+    nm = sc.image_texture(np.array([[[0.5, 0.5, 1.0, 1.0]]]))
+    pbr = sc.pbr(sc.constant_texture((0.5, 0.5, 0.5)), normal=nm)
+    sc.triangles(np.array([[(0, 0, 0), (-1, 0, 0), (0, 1, 0)]], dtype=np.float64), pbr, np.array([[(0, 0), (1, 0), (0, 1)]], dtype=np.float64))
+    h = oracle_mod.OracleScene(sc).hit((-0.25, 0.25, 5.0), (0, 0, -1), 0.0)
+    assert h is not None and h["t"] == 5.0
+    np.testing.assert_array_equal(h["normal"], [0, 0, -1])
+    np.testing.assert_allclose([h["u"], h["v"]], [0.25, 0.25], rtol=1e-15)
+
+
+@pytest.mark.parametrize("make,lo,hi", [
+    (lambda sc: sc.spectral_gaussian(1.0, 550, 40), 1.0, 1.0),             # peak at the centre wavelength
+    (lambda sc: sc.spectral_neutral(0.73), 0.73, 0.73),
+    (lambda sc: sc.spectral_tabulated([380, 500, 600, 750], [0.1, 0.5, 0.8, 0.3]), 0.65, 0.65),  # lerp(500->600) at 550
+])
+def test_spectral_texture_values_at_550(oracle_mod, make, lo, hi):
+    """transport/transport_test.go:193-274 evaluates each spectral texture kind at 550 nm (>= 0); the exact values
+    follow from spectral_constant.go:65-106."""
+    sc = SceneSpec(world_kind=S.WORLD_SLICE)
+    t = make(sc)
+    sc.sphere((0, 0, 0), 1, sc.spectral_lambertian(t))
+    v = oracle_mod.OracleScene(sc).spectral_texture_value(t, 550.0)
+    assert v >= 0 and lo - 1e-12 <= v <= hi + 1e-12
