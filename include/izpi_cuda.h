@@ -145,6 +145,8 @@ int izpi_debug_ray_aabb4(izpi_ctx* ctx, int32_t n, const float* org, const float
 /* ---- tile rendering --------------------------------------------------------------------- */
 #define IZPI_SAMPLER_COLOUR 0   /* sampler/colour.go   */
 #define IZPI_SAMPLER_SPECTRAL 1 /* sampler/spectral.go */
+#define IZPI_SAMPLER_ALBEDO 2   /* sampler/albedo.go: material albedo at the first hit, black on a miss */
+#define IZPI_SAMPLER_NORMAL 3   /* sampler/normal.go: hit-record normal at the first hit */
 
 typedef struct izpi_render_config {
   int32_t width, height, spp, max_depth;

@@ -142,7 +142,7 @@ __global__ void raygen_kernel(const __grid_constant__ DScene sc, RenderParams rp
 
 // terminal value of a path: what the pixel loop adds for this sample
 __device__ __forceinline__ void finish_path(const RenderParams& rp, PathState& p, d3 acc) {
-  if (rp.sampler == IZPI_SAMPLER_COLOUR) {  // vec3.DeNAN (rgb.go:36, vec3.go:141-158)
+  if (rp.sampler != IZPI_SAMPLER_SPECTRAL) {  // vec3.DeNAN (rgb.go:36, vec3.go:141-158)
     p.ax = isfinite(acc.x) ? acc.x : 0.0; p.ay = isfinite(acc.y) ? acc.y : 0.0; p.az = isfinite(acc.z) ? acc.z : 0.0;
   } else {  // render/spectral.go:91-95: XYZ += radiance * cmf / pdf, no DeNAN
     d3 cmf = cie_values(p.lambda);
@@ -152,6 +152,7 @@ __device__ __forceinline__ void finish_path(const RenderParams& rp, PathState& p
 }
 
 __device__ __forceinline__ d3 background_term(const RenderParams& rp, double lambda) {
+  if (rp.sampler >= IZPI_SAMPLER_ALBEDO) return mk(0, 0, 0);  // albedo.go:35, normal.go:33: a miss is black
   if (rp.sampler == IZPI_SAMPLER_COLOUR) return mk(rp.background[0], rp.background[1], rp.background[2]);
   double v = rp.n_bg > 0 ? spd_value(rp.bg_w, rp.bg_v, rp.n_bg, lambda) : 0.0;  // colours.SpectralBlack
   return mk(v, 0, 0);
@@ -178,7 +179,7 @@ extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* pat
     if (i < n) {
       pi = q.cur[i];
       PathState& p = paths[pi];
-      if (p.depth >= rp.max_depth) {
+      if (p.depth >= rp.max_depth && rp.sampler <= IZPI_SAMPLER_SPECTRAL) {
         // colour.go:34-36 returns (0,0,1); spectral.go:48-51 returns the background SPD
         d3 term = rp.sampler == IZPI_SAMPLER_COLOUR ? mk(0, 0, 1.0) : background_term(rp, p.lambda);
         d3 beta = mk(p.bx, p.by, p.bz), acc = mk(p.ax, p.ay, p.az);
@@ -242,7 +243,7 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
       if (s.cur == kIdle && chunk_next + before < chunk_end) {
         pi = q.cur[chunk_next + before];
         PathState& p = paths[pi];
-        if (p.depth >= rp.max_depth) {  // colour.go:34-36 / spectral.go:48-51
+        if (p.depth >= rp.max_depth && rp.sampler <= IZPI_SAMPLER_SPECTRAL) {  // colour.go:34-36 / spectral.go:48-51
           if (j == 0) {
             d3 term = rp.sampler == IZPI_SAMPLER_COLOUR ? mk(0, 0, 1.0) : background_term(rp, p.lambda);
             finish_path(rp, p, mk(p.ax, p.ay, p.az) + hadamard(mk(p.bx, p.by, p.bz), term));
@@ -391,6 +392,14 @@ shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* path
       DHit h;
       prim_hit<true>(sc, p.hit_rec, pr, r, 0.001, DBL_MAX, h);
       h.t = p.hit_t;
+      if (rp.sampler >= IZPI_SAMPLER_ALBEDO) {  // debug AOVs: one hit, no bounce (sampler/albedo.go:30-36, normal.go:28-34)
+        d3 aov;
+        if (rp.sampler == IZPI_SAMPLER_NORMAL) aov = h.n;
+        else if (CLS == IZPI_MAT_METAL) aov = mk(m.v[0], m.v[1], m.v[2]);             // metal.go:50
+        else if (CLS == IZPI_MAT_DIELECTRIC) aov = mk(1.0, 1.0, 1.0);                  // dielectric.go:223
+        else aov = m.tex >= 0 ? texture_value(sc, m.tex, h.u, h.v) : mk(0, 0, 0);      // lambertian.go:84, diffuselight.go:70, pbr.go:281
+        finish_path(rp, p, aov);
+      } else {
       Rng rng;
       rng.key = p.key; rng.ctr = p.ctr;
       d3 beta = mk(p.bx, p.by, p.bz), acc = mk(p.ax, p.ay, p.az);
@@ -471,6 +480,7 @@ shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* path
         p.bx = beta.x; p.by = beta.y; p.bz = beta.z; p.ax = acc.x; p.ay = acc.y; p.az = acc.z;
         p.key = rng.key; p.ctr = rng.ctr; p.depth = p.depth + 1;
       }
+      }  // integrators
     }
     push_binned(survive, 0, pi, q.next, q.capacity, q.counters + 1);
   }
@@ -508,7 +518,7 @@ __global__ void mean_kernel(RenderParams rp, const double* __restrict__ sums, do
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n_px) return;
   double a = sums[4 * i], b = sums[4 * i + 1], c = sums[4 * i + 2];
-  if (rp.sampler == IZPI_SAMPLER_COLOUR) { a = a / (double)rp.spp; b = b / (double)rp.spp; c = c / (double)rp.spp; }
+  if (rp.sampler != IZPI_SAMPLER_SPECTRAL) { a = a / (double)rp.spp; b = b / (double)rp.spp; c = c / (double)rp.spp; }
   else { double inv = 1.0 / (double)rp.spp; a = a * inv; b = b * inv; c = c * inv; }
   out[4 * i] = a; out[4 * i + 1] = b; out[4 * i + 2] = c; out[4 * i + 3] = sums[4 * i + 3];
 }
@@ -757,11 +767,11 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
   if (!ctx->has_scene) { set_error("izpi_render_setup: no scene uploaded"); return IZPI_ESTATE; }
   if (cfg->width <= 0 || cfg->height <= 0 || cfg->width > 65535 || cfg->height > 65535 || cfg->spp <= 0 || cfg->max_depth < 0 ||
       cfg->sample_count < 0 || cfg->sample_offset < 0 || cfg->sample_offset + cfg->sample_count > cfg->spp ||
-      (cfg->sampler != IZPI_SAMPLER_COLOUR && cfg->sampler != IZPI_SAMPLER_SPECTRAL)) {
+      cfg->sampler < IZPI_SAMPLER_COLOUR || cfg->sampler > IZPI_SAMPLER_NORMAL) {
     set_error("izpi_render_setup: invalid configuration");
     return IZPI_EINVAL;
   }
-  if (ctx->scene.n_lights == 0) {  // HitableSlice.Random indexes an empty slice: the reference panics
+  if (ctx->scene.n_lights == 0 && cfg->sampler <= IZPI_SAMPLER_SPECTRAL) {  // HitableSlice.Random indexes an empty slice: the reference panics
     set_error("izpi_render_setup: scene has no emitters (scene.Lights is empty)");
     return IZPI_EINVAL;
   }

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libizpi_cuda.so")
 
 OK, EINVAL, ECUDA, ESTATE = 0, -1, -2, -3
 TRACE_EXACT, TRACE_FP32 = 0, 1
-SAMPLER_COLOUR, SAMPLER_SPECTRAL = 0, 1
+SAMPLER_COLOUR, SAMPLER_SPECTRAL, SAMPLER_ALBEDO, SAMPLER_NORMAL = 0, 1, 2, 3
 
 
 class IzpiError(RuntimeError):

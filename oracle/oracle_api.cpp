@@ -250,7 +250,17 @@ void oracle_render(const oracle_scene* s, const oracle_render_params* p, double*
             ctr.mode = 1; ctr.key = Rng::stream_key(p->seed, (uint64_t)y * (uint64_t)nx + (uint64_t)x, (uint64_t)smpl); ctr.ctr = 0;
             r = &ctr; cr = &ctr;
           }
-          if (p->sampler == 0) {  // rgb.go:30-37
+          if (p->sampler >= 2) {  // sampler/albedo.go:30-36, sampler/normal.go:28-34 through the RGB pixel loop
+            double u = ((double)x + r->Float64()) / (double)nx;
+            double v = ((double)y + r->Float64()) / (double)ny;
+            Ray ray = cam.GetRay(u, v, 0, *cr);
+            smp.numRays++;
+            HitRecord rec; const Material* mat;
+            Vec3 c;
+            if (s->world.Hit(ray, 0.001, DBL_MAX, rec, mat)) c = p->sampler == 2 ? mat->Albedo(rec.u, rec.v) : rec.normal;
+            c = DeNAN(c);
+            a0 = a0 + c.X; a1 = a1 + c.Y; a2 = a2 + c.Z;
+          } else if (p->sampler == 0) {  // rgb.go:30-37
             double u = ((double)x + r->Float64()) / (double)nx;
             double v = ((double)y + r->Float64()) / (double)ny;
             Ray ray = cam.GetRay(u, v, 0, *cr);
@@ -269,7 +279,7 @@ void oracle_render(const oracle_scene* s, const oracle_render_params* p, double*
             a0 += (radiance * cx) / pdf; a1 += (radiance * cy) / pdf; a2 += (radiance * cz) / pdf;
           }
         }
-        if (p->sampler == 0) { a0 = a0 / (double)p->spp; a1 = a1 / (double)p->spp; a2 = a2 / (double)p->spp; }  // rgb.go:39
+        if (p->sampler != 1) { a0 = a0 / (double)p->spp; a1 = a1 / (double)p->spp; a2 = a2 / (double)p->spp; }  // rgb.go:39
         else { double inv = 1.0 / (double)p->spp; a0 = a0 * inv; a1 = a1 * inv; a2 = a2 * inv; }             // spectral.go:99-103
         int row = ny - y;  // rgb.go:41: canvas.Set(x, ny-y, ...); row ny is out of bounds -> dropped
         if (row >= 0 && row < ny) {

@@ -366,6 +366,12 @@ struct Material {
     return 0;
   }
 
+  Vec3 Albedo(double u, double vv) const {  // lambertian.go:84, metal.go:50, dielectric.go:223, diffuselight.go:70, pbr.go:281
+    if (type == IZPI_MAT_METAL) return v;
+    if (type == IZPI_MAT_DIELECTRIC) return V(1.0, 1.0, 1.0);
+    return tex ? tex->Value(u, vv) : Vec3();
+  }
+
   Vec3 Emitted(const Ray& rIn, const HitRecord& rec) const {  // diffuselight.go:49-55
     if (type == IZPI_MAT_DIFFUSE_LIGHT && Dot(rec.normal, rIn.direction) < 0.0) return tex->Value(rec.u, rec.v);
     return Vec3();

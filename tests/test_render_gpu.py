@@ -152,3 +152,11 @@ def test_spectral_pbr_image_albedo_same_path(ctx, oracle_mod):
     tv, tuv = scenes.torus_mesh(60, 40, centre=(50.0, 60.0, 50.0), major=30.0, minor=12.0, amp=3.0, scale=0.5)
     sc.triangles(tv, pbr, tuv)
     _same_path(ctx, oracle_mod, sc, 40, 40, 16, cuda.SAMPLER_SPECTRAL, min_close=0.93)
+
+
+@pytest.mark.parametrize("sampler", [cuda.SAMPLER_ALBEDO, cuda.SAMPLER_NORMAL], ids=["albedo", "normal"])
+def test_aov_samplers_same_path(ctx, oracle_mod, sampler):
+    """Debug AOV samplers (sampler/albedo.go, sampler/normal.go): first-hit albedo / normal, black on a miss."""
+    for spec in (scenes.cornell_box(1.0), scenes.cornell_pbr_mesh(1.0, n_around=60, n_tube=40, tex_size=64)):
+        img, ref, frac = _same_path(ctx, oracle_mod, spec, 40, 40, 4, sampler, min_close=0.995)
+        assert np.abs(img[1:, :, :3]).max() > 0
