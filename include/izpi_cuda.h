@@ -135,6 +135,17 @@ int izpi_trace_closest_device(izpi_ctx* ctx, int64_t n, const double* d_org_xyz,
 /* Counts the kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t izpi_launch_count(const izpi_ctx* ctx);
 
+/* ---- displacement tessellation -------------------------------------------------------------
+ * displacement.ApplyDisplacementMap(triangles, displacementMap, min, max) (internal/displacement/displacement.go:145):
+ * adaptive 1->4 tessellation until a triangle spans <= 4 texels of the map and its displacement variation is under
+ * the threshold, then TBN displacement of every vertex.  tris15: n x {v0.xyz v1.xyz v2.xyz u0 v0 u1 v1 u2 v2};
+ * the map is a W x H fp64 RGBA image whose BLUE channel is the height (image.go:73-101, displacement.go:108-110).
+ * per_triangle != 0 reproduces transport.go:633-646 (one call per input triangle, results concatenated);
+ * 0 = one call on the whole list.  The result stays on the device until fetched. */
+int izpi_displace(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t* materials, int32_t tex_w, int32_t tex_h,
+                  const double* pixels_rgba, double min, double max, int per_triangle, int64_t* n_out);
+int izpi_displace_fetch(izpi_ctx* ctx, double* out_tris15, int32_t* out_materials);
+
 /* Diagnostic (not part of the drop-in surface): the 4-wide fp32 slab test alone, n independent
  * cases -- RayAABB4_SIMD (bvh4_simd_amd64.go:27) -- so the reference's golden masks
  * (bvh4_simd_test.go:54-268) can be replayed on the device.  org/inv: n*3 floats; bounds: n*24 floats

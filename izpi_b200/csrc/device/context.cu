@@ -6,7 +6,8 @@
 
 using namespace izpi;
 
-void render_state_free(izpi_ctx* ctx);  // render.cu
+void render_state_free(izpi_ctx* ctx);    // render.cu
+void displace_result_free(izpi_ctx* ctx);  // displace.cu
 
 namespace {
 
@@ -68,6 +69,7 @@ void izpi_ctx_destroy(izpi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   render_state_free(ctx);
+  displace_result_free(ctx);
   free_scene(ctx);
   cudaFree(ctx->d_org); cudaFree(ctx->d_dir); cudaFree(ctx->d_ids); cudaFree(ctx->d_t); cudaFree(ctx->d_counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);

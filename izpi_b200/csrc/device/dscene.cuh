@@ -72,4 +72,5 @@ struct izpi_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint64_t launches = 0;
   RenderState* render = nullptr;
+  void* displace = nullptr;  // result of the last izpi_displace (displace.cu)
 };

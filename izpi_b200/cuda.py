@@ -42,7 +42,7 @@ class RenderConfig(C.Structure):
 EXPORTS = [
     "izpi_last_error", "izpi_version", "izpi_ctx_create", "izpi_ctx_destroy", "izpi_scene_upload",
     "izpi_trace_closest", "izpi_trace_closest_device", "izpi_launch_count", "izpi_render_setup", "izpi_render_tiles",
-    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4",
+    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_displace", "izpi_displace_fetch",
     "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
     "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
     "izpi_host_tiles", "izpi_host_render",
@@ -72,6 +72,9 @@ def lib():
     L.izpi_launch_count.argtypes = [C.c_void_p]
     L.izpi_launch_count.restype = C.c_uint64
     L.izpi_debug_ray_aabb4.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.izpi_displace.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_double,
+                                C.c_int, C.POINTER(C.c_int64)]
+    L.izpi_displace_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.izpi_render_setup.argtypes = [C.c_void_p, C.POINTER(RenderConfig)]
     L.izpi_render_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.izpi_render_canvas_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -186,6 +189,21 @@ class Context:
                              mode=TRACE_EXACT, stream=0):
         """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on `stream`."""
         check(lib().izpi_trace_closest_device(self._h, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, stream or None))
+
+    # ---- displacement.ApplyDisplacementMap ---------------------------------------------------
+    def apply_displacement(self, tris15, materials, pixels, dmin, dmax, per_triangle=True):
+        """tris15 (n,15) = v0 v1 v2 u0 v0 u1 v1 u2 v2; pixels (H,W,4) fp64 with the height in the blue channel.
+        Returns (out_tris15 (m,15), out_materials (m,))."""
+        t = np.ascontiguousarray(tris15, dtype=np.float64).reshape(-1, 15)
+        mats = np.ascontiguousarray(materials, dtype=np.int32).reshape(-1)
+        px = np.ascontiguousarray(pixels, dtype=np.float64)
+        n_out = C.c_int64()
+        check(lib().izpi_displace(self._h, len(t), t.ctypes.data, mats.ctypes.data, px.shape[1], px.shape[0], px.ctypes.data,
+                                  float(dmin), float(dmax), int(per_triangle), C.byref(n_out)))
+        out = np.empty((n_out.value, 15), dtype=np.float64)
+        om = np.empty(n_out.value, dtype=np.int32)
+        check(lib().izpi_displace_fetch(self._h, out.ctypes.data, om.ctypes.data))
+        return out, om
 
     def debug_ray_aabb4(self, org, inv, bounds, tmax):
         o = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)

@@ -76,6 +76,10 @@ def lib():
         L.oracle_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_firefly_rejection.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.oracle_xyz_to_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double]
+        L.oracle_apply_displacement.restype = C.c_int64
+        L.oracle_apply_displacement.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_double,
+                                                C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.oracle_free.argtypes = [C.c_void_p]
         L.oracle_tiles.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
@@ -92,6 +96,21 @@ def tiles(sx, sy):
     a, b = C.c_int32(), C.c_int32()
     lib().oracle_tiles(sx, sy, C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def apply_displacement(tris15, materials, pixels, dmin, dmax, per_triangle=True):
+    """displacement.ApplyDisplacementMap (displacement.go:145) as restated by the oracle."""
+    t = np.ascontiguousarray(tris15, dtype=np.float64).reshape(-1, 15)
+    mats = np.ascontiguousarray(materials, dtype=np.int32).reshape(-1)
+    px = np.ascontiguousarray(pixels, dtype=np.float64)
+    ot, om = C.c_void_p(), C.c_void_p()
+    k = lib().oracle_apply_displacement(len(t), t.ctypes.data, mats.ctypes.data, px.shape[1], px.shape[0], px.ctypes.data, float(dmin),
+                                        float(dmax), int(per_triangle), C.byref(ot), C.byref(om))
+    out = np.ctypeslib.as_array(C.cast(ot, C.POINTER(C.c_double)), shape=(max(k, 1) * 15,))[: k * 15].reshape(k, 15).copy()
+    outm = np.ctypeslib.as_array(C.cast(om, C.POINTER(C.c_int32)), shape=(max(k, 1),))[:k].copy()
+    lib().oracle_free(ot)
+    lib().oracle_free(om)
+    return out, outm
 
 
 class OracleScene:

@@ -6,6 +6,7 @@
 #include "oracle_shade.hpp"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -442,4 +443,96 @@ void oracle_probe_dielectric_test(int kind, double* out) {
   }
   out[0] = it; out[1] = foundA; out[2] = foundN;
 }
+}
+
+// ---- displacement.ApplyDisplacementMap (internal/displacement/displacement.go:36-280) ------------------------------
+namespace {
+struct MinimalTriangle {  // displacement.go:19-33
+  Vec3 vertex0, vertex1, vertex2;
+  int32_t material;
+  double u0, u1, u2, v0, v1, v2;
+};
+void tessellate(const MinimalTriangle& in, MinimalTriangle out[4]) {  // displacement.go:36-103
+  Vec3 a = ScalarDiv(Add(in.vertex0, in.vertex1), 2.0), b = ScalarDiv(Add(in.vertex1, in.vertex2), 2.0), c = ScalarDiv(Add(in.vertex2, in.vertex0), 2.0);
+  double ua = (in.u0 + in.u1) / 2.0, va = (in.v0 + in.v1) / 2.0, ub = (in.u1 + in.u2) / 2.0, vb = (in.v1 + in.v2) / 2.0;
+  double uc = (in.u2 + in.u0) / 2.0, vc = (in.v2 + in.v0) / 2.0;
+  out[0] = {in.vertex0, a, c, in.material, in.u0, ua, uc, in.v0, va, vc};
+  out[1] = {a, b, c, in.material, ua, ub, uc, va, vb, vc};
+  out[2] = {a, in.vertex1, b, in.material, ua, in.u1, ub, va, in.v1, vb};
+  out[3] = {c, b, in.vertex2, in.material, uc, ub, in.u2, vc, vb, in.v2};
+}
+bool isTessellatedEnough(const MinimalTriangle& t, double maxDeltaU, double maxDeltaV, const Texture& map, double mn, double mx,
+                         double adaptiveThreshold) {  // displacement.go:120-141
+  bool uv = std::fabs(t.u1 - t.u0) <= maxDeltaU && std::fabs(t.u2 - t.u1) <= maxDeltaU && std::fabs(t.u0 - t.u2) <= maxDeltaU &&
+            std::fabs(t.v1 - t.v0) <= maxDeltaV && std::fabs(t.v2 - t.v1) <= maxDeltaV && std::fabs(t.v0 - t.v2) <= maxDeltaV;
+  if (!uv) return false;
+  double d0 = map.Value(t.u0, t.v0).Z, d1 = map.Value(t.u1, t.v1).Z, d2 = map.Value(t.u2, t.v2).Z;  // :106-118
+  double variation = gomax(d0, gomax(d1, d2)) - gomin(d0, gomin(d1, d2));
+  return variation * std::fabs(mx - mn) <= adaptiveThreshold;
+}
+void displaceOne(const MinimalTriangle& t, const Texture& map, double mn, double mx, double out15[15]) {  // displacement.go:201-280
+  Vec3 edge1 = Sub(t.vertex1, t.vertex0), edge2 = Sub(t.vertex2, t.vertex0);
+  Vec3 normal = MakeUnitVector(Cross(edge1, edge2));
+  double dU1 = t.u1 - t.u0, dU2 = t.u2 - t.u0, dV1 = t.v1 - t.v0, dV2 = t.v2 - t.v0;
+  double f = 1.0 / (dU1 * dV2 - dU2 * dV1);
+  Vec3 tangent = MakeUnitVector(V(f * (dV2 * edge1.X - dV1 * edge2.X), f * (dV2 * edge1.Y - dV1 * edge2.Y), f * (dV2 * edge1.Z - dV1 * edge2.Z)));
+  Vec3 bitangent = MakeUnitVector(V(f * (-dU2 * edge1.X + dU1 * edge2.X), f * (-dU2 * edge1.Y + dU1 * edge2.Y), f * (-dU2 * edge1.Z + dU1 * edge2.Z)));
+  auto disp = [&](const Vec3& vtx, double u, double v) {
+    double z = mn + ((mx - mn) * map.Value(u, v).Z);
+    // mat3.MatrixVectorMul(tbn, (0, 0, z)) (mat3.go:34): every row keeps its three products
+    Vec3 d = V(tangent.X * 0.0 + bitangent.X * 0.0 + normal.X * z, tangent.Y * 0.0 + bitangent.Y * 0.0 + normal.Y * z,
+               tangent.Z * 0.0 + bitangent.Z * 0.0 + normal.Z * z);
+    return Add(vtx, d);
+  };
+  Vec3 p0 = disp(t.vertex0, t.u0, t.v0), p1 = disp(t.vertex1, t.u1, t.v1), p2 = disp(t.vertex2, t.u2, t.v2);
+  double o[15] = {p0.X, p0.Y, p0.Z, p1.X, p1.Y, p1.Z, p2.X, p2.Y, p2.Z, t.u0, t.v0, t.u1, t.v1, t.u2, t.v2};
+  std::memcpy(out15, o, sizeof(o));
+}
+void applyOne(std::vector<MinimalTriangle> in, const Texture& map, double mn, double mx, std::vector<double>& out, std::vector<int32_t>& mats) {
+  double maxDeltaU = 4.0 / (double)(map.sizeX - 1), maxDeltaV = 4.0 / (double)(map.sizeY - 1);  // displacement.go:176-178
+  const double adaptiveThreshold = 2.0;
+  std::vector<MinimalTriangle> done;
+  int level = 0;
+  while (!in.empty()) {  // applyTessellation (displacement.go:188-218)
+    // (the reference loops forever when two ADJACENT texels differ by more than threshold/|max-min|: a triangle
+    // straddling them never passes; such maps are invalid inputs and are cut off here)
+    if (++level > 40 || in.size() > (1u << 28)) { in.clear(); break; }
+    std::vector<MinimalTriangle> toIn;
+    for (const MinimalTriangle& t : in) {
+      MinimalTriangle ch[4];
+      tessellate(t, ch);
+      for (int k = 0; k < 4; k++) (isTessellatedEnough(ch[k], maxDeltaU, maxDeltaV, map, mn, mx, adaptiveThreshold) ? done : toIn).push_back(ch[k]);
+    }
+    in.swap(toIn);
+  }
+  for (const MinimalTriangle& t : done) {
+    double o[15];
+    displaceOne(t, map, mn, mx, o);
+    out.insert(out.end(), o, o + 15);
+    mats.push_back(t.material);
+  }
+}
+}  // namespace
+
+extern "C" {
+// tris: n x 15 doubles (v0 v1 v2 u0 v0 u1 v1 u2 v2).  per_triangle != 0 = the transport call shape: one
+// ApplyDisplacementMap call per input triangle, results concatenated (transport.go:633-646).
+// Returns the number of output triangles; *out_tris / *out_mats are malloc'ed (free with oracle_free).
+int64_t oracle_apply_displacement(int64_t n, const double* tris, const int32_t* mats, int32_t w, int32_t h, const double* pixels,
+                                  double mn, double mx, int per_triangle, double** out_tris, int32_t** out_mats) {
+  Texture map; map.type = IZPI_TEX_IMAGE; map.sizeX = w; map.sizeY = h; map.pixels = pixels;
+  std::vector<double> out; std::vector<int32_t> om;
+  auto mk1 = [&](int64_t i) {
+    const double* p = tris + 15 * i;
+    return MinimalTriangle{V(p[0], p[1], p[2]), V(p[3], p[4], p[5]), V(p[6], p[7], p[8]), mats ? mats[i] : 0, p[9], p[11], p[13], p[10], p[12], p[14]};
+  };
+  if (per_triangle) { for (int64_t i = 0; i < n; i++) applyOne({mk1(i)}, map, mn, mx, out, om); }
+  else { std::vector<MinimalTriangle> in; for (int64_t i = 0; i < n; i++) in.push_back(mk1(i)); applyOne(in, map, mn, mx, out, om); }
+  *out_tris = (double*)std::malloc(out.size() * sizeof(double) + 8);
+  *out_mats = (int32_t*)std::malloc(om.size() * sizeof(int32_t) + 8);
+  std::memcpy(*out_tris, out.data(), out.size() * sizeof(double));
+  std::memcpy(*out_mats, om.data(), om.size() * sizeof(int32_t));
+  return (int64_t)om.size();
+}
+void oracle_free(void* p) { std::free(p); }
 }
