@@ -100,8 +100,8 @@ def bench_render(ctx, cuda, scenes, world, rank, barrier, with_4k=True):
              ("config 4 scene: spectral glass pyramid 1024x1024 at 16 spp (BASELINE: 1024 spp)", lambda: scenes.spectral_pyramid(1.0), 1024, 1024,
               16, cuda.SAMPLER_SPECTRAL)]
     if with_4k:  # the multi-GPU target of BASELINE: a 4K render, tile-sharded
-        cases.append(("config 5 scene: 4K IBL + ~10M-triangle mesh 3840x2160 at 16 spp (BASELINE: 1024 spp)",
-                      lambda: scenes.ibl_displaced_mesh(3840 / 2160), 3840, 2160, 16, cuda.SAMPLER_COLOUR))
+        cases.append(("config 5 scene: 4K IBL + displacement-tessellated 11.5M-triangle mesh 3840x2160 at 16 spp (BASELINE: 1024 spp)",
+                      lambda: scenes.ibl_tessellated_mesh(ctx, 3840 / 2160)[0], 3840, 2160, 16, cuda.SAMPLER_COLOUR))
     for name, make, w, h, spp, sampler in cases:
         spec = make()
         ctx.upload(cuda.HostScene(spec, threads=max(1, (os.cpu_count() or 8) // world)))

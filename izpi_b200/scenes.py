@@ -248,6 +248,46 @@ def ibl_displaced_mesh(aspect: float = 3840 / 2160, n_around: int = 3162, n_tube
     return sc
 
 
+def height_map(width: int = 4096, height: int = 2048):
+    """Smooth synthetic displacement map (fp64 RGBA, height in the blue channel as displacement.go:108-110 reads it).
+    Band-limited, so adjacent texels differ by far less than the tessellator's adaptive threshold allows."""
+    u = (np.arange(width) + 0.5) / width
+    v = (np.arange(height) + 0.5) / height
+    U, V = np.meshgrid(u, v)
+    z = (0.5 + 0.25 * np.sin(2 * np.pi * 6 * U) * np.cos(2 * np.pi * 5 * V) + 0.15 * np.sin(2 * np.pi * 17 * U + 1) * np.sin(2 * np.pi * 13 * V)
+         + 0.1 * np.sin(2 * np.pi * 37 * U) * np.cos(2 * np.pi * 29 * V + 2))
+    px = np.ones((height, width, 4))
+    px[..., 2] = z
+    return px
+
+
+def ibl_tessellated_mesh(ctx, aspect: float = 3840 / 2160, n_around: int = 160, n_tube: int = 80, map_size=(5632, 2816),
+                         range_fraction: float = 0.9, env_size=(4096, 2048), bvh_seed: int = 12345):
+    """Config 5 as BASELINE words it: image-based-lit scene with a DISPLACEMENT-TESSELLATED mesh.  A coarse torus
+    (2*n_around*n_tube triangles, proto-style fp32 vertices) goes through displacement.ApplyDisplacementMap
+    (run on the device, izpi_displace) with a smooth height map, one call per base triangle as transport.go:633-646
+    does; the displacement range is `range_fraction` of the largest range for which the reference's adaptive loop
+    terminates on this map (threshold 2.0 / largest adjacent-texel step).  Returns (SceneSpec, n_triangles).
+    The scene is scaled so that the fixed world-space threshold of displacement.go:183 is meaningful
+    (torus radii 600 / 240, displacement range a fraction of the tube radius)."""
+    px = height_map(*map_size)
+    step = max(np.abs(np.diff(px[..., 2], axis=0)).max(), np.abs(np.diff(px[..., 2], axis=1)).max())
+    rng = range_fraction * 2.0 / step
+    verts, uvs = torus_mesh(n_around, n_tube, centre=(0.0, 0.0, 0.0), major=600.0, minor=240.0, amp=0.0)
+    base = np.concatenate([verts.reshape(-1, 9), uvs.reshape(-1, 6)], axis=1)
+    sc = SceneSpec(world_kind=S.WORLD_BVH4, bvh_seed=bvh_seed)
+    metal = sc.metal(f32((0.92, 0.86, 0.78)), f32(0.03))
+    glass = sc.dielectric(f32(1.5))
+    sky = sc.diffuse_light(sc.image_texture(sky_texture(*env_size)))
+    tris, mats = ctx.apply_displacement(base, np.full(len(base), metal, dtype=np.int32), px, -rng / 2, rng / 2, per_triangle=True)
+    sc.triangles(tris[:, :9].reshape(-1, 3, 3), mats, tris[:, 9:].reshape(-1, 3, 2))
+    sc.sphere(f32((0.0, 480.0, 0.0)), float(f32(180.0)), glass)
+    sc.sphere(f32((0.0, 0.0, 0.0)), float(f32(10000.0)), sky)
+    sc.prims["wrap"][-1] = S.WRAP_FLIP
+    sc.set_camera(f32((1400, 900, 1900)), f32((0, 40, 0)), f32((0, 1, 0)), f32(38), aspect, f32(0), f32(10), f32(0), f32(1), f32(1.0))
+    return sc, len(tris)
+
+
 _CORNELL_RGB = {"White": (0.73, 0.73, 0.73), "Green": (0, 0.73, 0), "Red": (0.73, 0, 0)}
 
 

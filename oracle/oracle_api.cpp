@@ -496,7 +496,7 @@ void applyOne(std::vector<MinimalTriangle> in, const Texture& map, double mn, do
   while (!in.empty()) {  // applyTessellation (displacement.go:188-218)
     // (the reference loops forever when two ADJACENT texels differ by more than threshold/|max-min|: a triangle
     // straddling them never passes; such maps are invalid inputs and are cut off here)
-    if (++level > 40 || in.size() > (1u << 28)) { in.clear(); break; }
+    if (++level > 40 || in.size() > (1u << 25)) { in.clear(); break; }
     std::vector<MinimalTriangle> toIn;
     for (const MinimalTriangle& t : in) {
       MinimalTriangle ch[4];

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--around", type=int, default=3162)
     ap.add_argument("--tube", type=int, default=1581)
     ap.add_argument("--checksum", action="store_true")
+    ap.add_argument("--tessellated", action="store_true", help="build the mesh with the displacement tessellator (izpi_displace) "
+                    "instead of the analytically displaced torus")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -38,13 +40,16 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = cuda.Context(local)
     t0 = time.perf_counter()
-    sc = scenes.ibl_displaced_mesh(args.width / args.height, args.around, args.tube)
+    if args.tessellated:
+        sc, n_tris = scenes.ibl_tessellated_mesh(ctx, args.width / args.height)
+    else:
+        sc, n_tris = scenes.ibl_displaced_mesh(args.width / args.height, args.around, args.tube), 2 * args.around * args.tube
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
     hs = cuda.HostScene(sc, threads=max(1, (os.cpu_count() or 8) // world))
     t_build = time.perf_counter() - t0
-    ctx = cuda.Context(local)
     t0 = time.perf_counter()
     ctx.upload(hs)
     t_up = time.perf_counter() - t0
@@ -65,7 +70,7 @@ def main():
         dt = float(tt.item())
     if rank == 0:
         n = args.width * args.height * args.spp
-        line = {"scene": "config 5: IBL + ~10M-triangle displaced mesh", "triangles": int(2 * args.around * args.tube), "width": args.width,
+        line = {"scene": "config 5: IBL + ~10M-triangle displaced mesh", "triangles": int(n_tris), "mesh": "displacement-tessellated (izpi_displace)" if args.tessellated else "analytic torus", "width": args.width,
                 "height": args.height, "spp": args.spp, "n_gpus": world, "msamples_per_s": n / dt / 1e6, "seconds": dt,
                 "mrays_per_s": r.num_rays / dt / 1e6, "rays_per_sample": r.num_rays / n, "scene_gen_s": t_gen,
                 "host_bvh_build_s": t_build, "upload_s": t_up, "mean_rgb": [float(x) for x in img[1:, :, :3].mean(axis=(0, 1))]}
