@@ -242,6 +242,23 @@ def main():
     # results of the two paths agree
     assert np.array_equal(np_ids, d_ids.cpu().numpy()) and np.array_equal(np_t, d_t.cpu().numpy())
 
+    # optional fp32-primitive mode, reported separately (BASELINE north_star): same traversal, fp32 triangle test
+    d_ids32 = torch.empty_like(d_ids)
+    d_t32 = torch.empty_like(d_t)
+    for _ in range(2):
+        ctx.trace_closest_device(n, d_org.data_ptr(), d_dir.data_ptr(), d_ids32.data_ptr(), d_t32.data_ptr(), mode=cuda.TRACE_FP32, stream=stream)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        ctx.trace_closest_device(n, d_org.data_ptr(), d_dir.data_ptr(), d_ids32.data_ptr(), d_t32.data_ptr(), mode=cuda.TRACE_FP32, stream=stream)
+    f1.record()
+    torch.cuda.synchronize()
+    fp32_ms = f0.elapsed_time(f1) / args.steps
+    step_device()
+    torch.cuda.synchronize()
+    fp32_info = {"value": n / (fp32_ms * 1e-3) / 1e6, "unit": "Mrays/s per GPU", "ids_equal_to_exact": float((d_ids32 == d_ids).double().mean().item()),
+                 "note": "fp32 Moeller-Trumbore, same BVH4 traversal; not part of the parity claim"}
+
     render_info = bench_render(ctx, cuda, scenes, world, rank, barrier, with_4k=not args.no_4k)
     ctx.upload(hs)  # back to the closest-hit scene for the CPU-baseline parity check below
 
@@ -267,6 +284,7 @@ def main():
                     "d2h_bytes_per_step": n * 12},
             "gpu_launches": int(launches),
             "render": render_info,
+            "fp32_mode": fp32_info,
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:

@@ -135,7 +135,27 @@ __device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2
 
 // Leaf phase: lane j tests primitive j; the group then replays the reference's sequential
 // `if hit { tMax = rec.T() }` loop (bvh4.go:125-134) over the four candidates.
-template <bool COUNT>
+// fp32 Moeller-Trumbore for the optional IZPI_TRACE_FP32 mode (reported separately, not bit-exact by design)
+__device__ __forceinline__ bool tri_test_f32(const PrimRec& pr, const double* rs, float tmin, float tmax, float& t) {
+  const float eps = 1e-8f;
+  float dx = (float)rs[3], dy = (float)rs[4], dz = (float)rs[5];
+  float e1x = (float)pr.a[3], e1y = (float)pr.a[4], e1z = (float)pr.a[5], e2x = (float)pr.a[6], e2y = (float)pr.a[7], e2z = (float)pr.a[8];
+  float hx = dy * e2z - dz * e2y, hy = -(dx * e2z - dz * e2x), hz = dx * e2y - dy * e2x;
+  float a = e1x * hx + e1y * hy + e1z * hz;
+  if (fabsf(a) < eps) return false;
+  float f = 1.0f / a;
+  // the origin difference is formed in fp64 first: both terms can be large and close
+  float sx = (float)(rs[0] - pr.a[0]), sy = (float)(rs[1] - pr.a[1]), sz = (float)(rs[2] - pr.a[2]);
+  float u = f * (sx * hx + sy * hy + sz * hz);
+  if (u < -eps || u > 1.0f + eps) return false;
+  float qx = sy * e1z - sz * e1y, qy = -(sx * e1z - sz * e1x), qz = sx * e1y - sy * e1x;
+  float v = f * (dx * qx + dy * qy + dz * qz);
+  if (v < -eps || u + v > 1.0f + eps) return false;
+  t = f * (e2x * qx + e2y * qy + e2z * qz);
+  return !(t < tmin || t > tmax);
+}
+
+template <bool COUNT, bool F32 = false>
 __device__ __forceinline__ void g4_leaf_phase(G4State& s, const DScene& sc, const int2* stack, unsigned lane, int gshift, int j,
                                               uint32_t& n_nodes, uint32_t& n_prims, double tmin) {
   const unsigned full = 0xffffffffu;
@@ -147,11 +167,17 @@ __device__ __forceinline__ void g4_leaf_phase(G4State& s, const DScene& sc, cons
   if (in_leaf && j < cnt) {
     PrimRec pr = load_rec(sc.prims + start + j);
     const double* rs = reinterpret_cast<const double*>(stack + kG4Stack);
-    DRay r;
-    r.o = mk(rs[0], rs[1], rs[2]); r.d = mk(rs[3], rs[4], rs[5]); r.time = 0; r.lambda = 0;
-    DHit h;
-    ok = prim_hit<false>(sc, start + j, pr, r, tmin, s.tmax, h);
-    t = h.t;
+    if (F32 && tag_type(pr.tag) == IZPI_PRIM_TRIANGLE && tag_xform(pr.tag) == 0) {
+      float tf = 0.0f;
+      ok = tri_test_f32(pr, rs, (float)tmin, (float)s.tmax, tf);
+      t = (double)tf;
+    } else {
+      DRay r;
+      r.o = mk(rs[0], rs[1], rs[2]); r.d = mk(rs[3], rs[4], rs[5]); r.time = 0; r.lambda = 0;
+      DHit h;
+      ok = prim_hit<false>(sc, start + j, pr, r, tmin, s.tmax, h);
+      t = h.t;
+    }
     strict = tag_type(pr.tag) == IZPI_PRIM_SPHERE;  // Sphere.Hit compares strictly (sphere.go:73,84)
     if (COUNT) n_prims++;
   }

@@ -55,7 +55,7 @@ constexpr int kChunk = 256;
 #define IZPI_G4_MIN_BLOCKS 6
 #endif
 
-template <bool COUNT>
+template <bool COUNT, bool F32>
 __global__ void __launch_bounds__(kTraceThreads, IZPI_G4_MIN_BLOCKS)
 trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __restrict__ org,
                 const double* __restrict__ dir, double tmin, double tmax, int32_t* __restrict__ ids,
@@ -106,7 +106,7 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
     }
     // ---- node phase, then leaf phase (both warp-uniform)
     g4_node_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, stragglers);
-    g4_leaf_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, n_prims, tmin);
+    g4_leaf_phase<COUNT, F32>(s, sc, stack, lane, gshift, j, n_nodes, n_prims, tmin);
     // ---- finished rays write their answer
     if (s.cur == kIdle && ray >= 0) {
       if (j == 0) {
@@ -137,15 +137,19 @@ __global__ void box4_kernel(int n, const float* __restrict__ org, const float* _
 
 int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir, double tmin, double tmax,
                  int mode, int32_t* d_ids, double* d_t, cudaStream_t st, bool count, unsigned long long* counters) {
-  if (mode != IZPI_TRACE_EXACT) { set_error("izpi_trace_closest: only IZPI_TRACE_EXACT is implemented"); return IZPI_EINVAL; }
+  if (mode != IZPI_TRACE_EXACT && mode != IZPI_TRACE_FP32) { set_error("izpi_trace_closest: unknown mode"); return IZPI_EINVAL; }
+  if (mode == IZPI_TRACE_FP32 && !(ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok)) {
+    set_error("izpi_trace_closest: IZPI_TRACE_FP32 needs a BVH4 world built by NewBVH4");
+    return IZPI_EINVAL;
+  }
   if (n > (1ll << 30)) { set_error("izpi_trace_closest: at most 2^30 rays per launch; split the batch"); return IZPI_EINVAL; }
   IZ_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), st));
-  if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar) {
+  if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && (!ctx->force_scalar || mode == IZPI_TRACE_FP32)) {
     size_t smem4 = (size_t)(kTraceThreads / 4) * kG4Slab * sizeof(int2);
-    auto k4 = count ? trace_g4_kernel<true> : trace_g4_kernel<false>;
+    auto k4 = mode == IZPI_TRACE_FP32 ? trace_g4_kernel<false, true> : (count ? trace_g4_kernel<true, false> : trace_g4_kernel<false, false>);
     static thread_local int bps4 = 0;
     if (!bps4) {
-      IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps4, trace_g4_kernel<false>, kTraceThreads, smem4));
+      IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps4, trace_g4_kernel<false, false>, kTraceThreads, smem4));
       if (bps4 < 1) bps4 = 1;
     }
     long long want4 = (n + (kTraceThreads / 4) - 1) / (kTraceThreads / 4);

@@ -167,3 +167,24 @@ def test_full_size_config2_properties(ctx, oracle_mod):
     s = slice(0, n, 256)
     oi, ot = osn.trace(org[s], d[s])
     assert oi.tobytes() == ids[s].tobytes() and ot.tobytes() == t[s].tobytes()
+
+
+def test_fp32_mode_agrees_closely(ctx, oracle_mod):
+    """Optional IZPI_TRACE_FP32 mode (fp32 triangle test): not bit-exact by design, reported separately; it must
+    still find the same primitive for nearly every ray and t to fp32 accuracy."""
+    verts, uvs = scenes.torus_mesh(300, 200)
+    sc = S.SceneSpec(bvh_seed=12345)
+    sc.triangles(verts, sc.lambertian(sc.constant_texture((0.5, 0.5, 0.5))), uvs)
+    lo, hi = verts.reshape(-1, 3).min(0), verts.reshape(-1, 3).max(0)
+    org, d = scenes.random_rays(1 << 17, lo, hi)
+    ctx.upload(cuda.HostScene(sc))
+    ids, t = ctx.trace_closest(org, d)
+    ids32, t32 = ctx.trace_closest(org, d, mode=cuda.TRACE_FP32)
+    same = ids == ids32
+    assert same.mean() > 0.999
+    hit = same & (ids >= 0)
+    assert np.allclose(t32[hit], t[hit], rtol=1e-4)
+    # a slice world has no fp32 path: loud error, no silent fallback
+    ctx.upload(cuda.HostScene(scenes.cornell_box()))
+    with pytest.raises(cuda.IzpiError):
+        ctx.trace_closest(org[:8], d[:8], mode=cuda.TRACE_FP32)
