@@ -51,6 +51,8 @@ class ClockSampler(threading.Thread):
         self.index, self.stop_flag, self.rows = index, threading.Event(), []
 
     def run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -60,6 +62,30 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
+
+    def _run_nvml(self):
+        """Same fields through NVML (nvidia_ml_py), sampled every 20 ms: a timed region of a few steps lasts well under a
+        second, which an nvidia-smi process per sample cannot resolve."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons(h)
+        except Exception:
+            return False
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.rows.append([str(sm), str(mx)] + [("Active" if r & b else "Not Active") for b in bits.values()])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+        return True
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
