@@ -146,6 +146,16 @@ int izpi_displace(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t*
                   const double* pixels_rgba, double min, double max, int per_triangle, int64_t* n_out);
 int izpi_displace_fetch(izpi_ctx* ctx, double* out_tris15, int32_t* out_materials);
 
+/* ---- device-side BVH4 build ------------------------------------------------------------------
+ * Optional replacement for hitable.NewBVH4 (internal/hitable/bvh4.go:517-855) when setup time matters: boxes6 =
+ * n x {min.xyz max.xyz}, the BoundingBox(time0, time1) of every hitable (fp64).  Builds a Morton-ordered LBVH on the
+ * GPU and collapses it into the reference's node format (128-byte BVH4Node, leaf-nodes using slot 0 only, boxes rounded
+ * outward to float32, leaves contiguous in the returned permutation: Primitives[i] = hitables[perm[i]]), so BVH4.Hit and
+ * every kernel here consume it unchanged.  The tree is NOT the reference's tree; closest hits are the same.  Fails if
+ * the tree could overflow the traversal's 64-entry stack (bvh4.go:71).  The result stays in the context until fetched. */
+int izpi_bvh4_build(izpi_ctx* ctx, int32_t n, const double* boxes6, int32_t* n_nodes);
+int izpi_bvh4_build_fetch(izpi_ctx* ctx, izpi_bvh4_node* nodes, int32_t* perm);
+
 /* Diagnostic (not part of the drop-in surface): the 4-wide fp32 slab test alone, n independent
  * cases -- RayAABB4_SIMD (bvh4_simd_amd64.go:27) -- so the reference's golden masks
  * (bvh4_simd_test.go:54-268) can be replayed on the device.  org/inv: n*3 floats; bounds: n*24 floats

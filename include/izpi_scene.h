@@ -116,6 +116,11 @@ enum {
   IZPI_WORLD_BVH4 = 1   /* world = HitableSlice{NewBVH4(prims)}   transport.go:76 */
 };
 
+enum {
+  IZPI_BVH_REFERENCE = 0,   /* random-axis median split, the reference's tree node for node (bvh4.go:558-855) */
+  IZPI_BVH_DEVICE_LBVH = 1  /* built on the GPU (Morton LBVH -> BVH4Node array); same closest hits, different tree */
+};
+
 typedef struct izpi_scene_spec {
   int32_t world_kind;
   int32_t n_prims;
@@ -134,7 +139,7 @@ typedef struct izpi_scene_spec {
    * bvh_rand_zero != 0 selects the tests' `func() float64 { return 0 }`. */
   uint64_t bvh_seed;
   int32_t bvh_rand_zero;
-  int32_t reserved2;
+  int32_t bvh_builder; /* IZPI_BVH_REFERENCE (hitable.NewBVH4 restated on the host) | IZPI_BVH_DEVICE_LBVH */
 } izpi_scene_spec;
 
 /* The reference's flat BVH4 node, byte for byte (hitable/bvh4.go:23-39). */

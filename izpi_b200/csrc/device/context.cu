@@ -8,6 +8,7 @@ using namespace izpi;
 
 void render_state_free(izpi_ctx* ctx);    // render.cu
 void displace_result_free(izpi_ctx* ctx);  // displace.cu
+void bvh_build_result_free(izpi_ctx* ctx);  // bvh_build.cu
 
 namespace {
 
@@ -70,6 +71,7 @@ void izpi_ctx_destroy(izpi_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   render_state_free(ctx);
   displace_result_free(ctx);
+  bvh_build_result_free(ctx);
   free_scene(ctx);
   cudaFree(ctx->d_org); cudaFree(ctx->d_dir); cudaFree(ctx->d_ids); cudaFree(ctx->d_t); cudaFree(ctx->d_counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -73,4 +73,5 @@ struct izpi_ctx {
   uint64_t launches = 0;
   RenderState* render = nullptr;
   void* displace = nullptr;  // result of the last izpi_displace (displace.cu)
+  void* bvh_build = nullptr;  // result of the last izpi_bvh4_build (bvh_build.cu)
 };

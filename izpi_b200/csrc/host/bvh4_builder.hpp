@@ -30,6 +30,10 @@ struct BVH4Build {
 // (fastrandom LCG constants, fastrandom.go:7-11; or the tests' constant 0, bvh4_test.go:57).
 BVH4Build NewBVH4(const std::vector<BoxD>& boxes, uint64_t seed, bool rand_zero, int threads);
 
+// Optional device build (csrc/device/bvh_build.cu): Morton-ordered LBVH collapsed into the same node format.  The tree
+// differs from the reference's; closest hits do not.  Empty result + izpi_last_error() on failure.
+BVH4Build BuildBVH4Device(const std::vector<BoxD>& boxes);
+
 float ConservativeFloat32Min(double v);  // bvh4.go:494
 float ConservativeFloat32Max(double v);  // bvh4.go:506
 

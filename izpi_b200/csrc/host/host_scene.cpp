@@ -184,7 +184,12 @@ int izpi_host_scene_create(const izpi_scene_spec* spec, int threads, izpi_host_s
   // world order
   std::vector<int32_t> rec_of(n);
   if (spec->world_kind == IZPI_WORLD_BVH4 && n > 0) {
-    s->bvh = NewBVH4(boxes, spec->bvh_seed, spec->bvh_rand_zero != 0, threads);  // transport.go:76
+    if (spec->bvh_builder == IZPI_BVH_DEVICE_LBVH) {
+      s->bvh = BuildBVH4Device(boxes);
+      if (s->bvh.nodes.empty()) { delete s; return IZPI_ECUDA; }  // message set by the builder; no host fallback
+    } else {
+      s->bvh = NewBVH4(boxes, spec->bvh_seed, spec->bvh_rand_zero != 0, threads);  // transport.go:76
+    }
     s->recs.resize(n); s->attrs.resize(n);
     for (int i = 0; i < n; i++) {
       int32_t src = s->bvh.perm[i];

@@ -42,7 +42,7 @@ class RenderConfig(C.Structure):
 EXPORTS = [
     "izpi_last_error", "izpi_version", "izpi_ctx_create", "izpi_ctx_destroy", "izpi_scene_upload",
     "izpi_trace_closest", "izpi_trace_closest_device", "izpi_launch_count", "izpi_render_setup", "izpi_render_tiles",
-    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_displace", "izpi_displace_fetch",
+    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_displace", "izpi_displace_fetch", "izpi_bvh4_build", "izpi_bvh4_build_fetch",
     "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
     "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
     "izpi_host_tiles", "izpi_host_render",
@@ -75,6 +75,8 @@ def lib():
     L.izpi_displace.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_double,
                                 C.c_int, C.POINTER(C.c_int64)]
     L.izpi_displace_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.izpi_bvh4_build.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
+    L.izpi_bvh4_build_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.izpi_render_setup.argtypes = [C.c_void_p, C.POINTER(RenderConfig)]
     L.izpi_render_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.izpi_render_canvas_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -204,6 +206,17 @@ class Context:
         om = np.empty(n_out.value, dtype=np.int32)
         check(lib().izpi_displace_fetch(self._h, out.ctypes.data, om.ctypes.data))
         return out, om
+
+    # ---- hitable.NewBVH4 on the device -----------------------------------------------------------
+    def build_bvh4(self, boxes6):
+        """boxes6 (n,6) = min.xyz max.xyz of every hitable.  Returns (BVH4.Nodes, permutation)."""
+        b = np.ascontiguousarray(boxes6, dtype=np.float64).reshape(-1, 6)
+        nn = C.c_int32()
+        check(lib().izpi_bvh4_build(self._h, len(b), b.ctypes.data, C.byref(nn)))
+        nodes = np.zeros(nn.value, dtype=NODE_DTYPE)
+        perm = np.zeros(len(b), dtype=np.int32)
+        check(lib().izpi_bvh4_build_fetch(self._h, nodes.ctypes.data, perm.ctypes.data))
+        return nodes, perm
 
     def debug_ray_aabb4(self, org, inv, bounds, tmax):
         o = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)

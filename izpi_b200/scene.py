@@ -18,6 +18,7 @@ TEX_CONSTANT, TEX_IMAGE = 0, 1
 SPEC_GAUSSIAN, SPEC_TABULATED, SPEC_IMAGE = 0, 1, 2
 MAT_LAMBERT, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_PBR = range(5)
 WORLD_SLICE, WORLD_BVH4 = 0, 1
+BVH_REFERENCE, BVH_DEVICE_LBVH = 0, 1
 
 PRIM_DTYPE = np.dtype(
     [("type", "<i4"), ("material", "<i4"), ("wrap", "<i4"), ("reserved", "<i4"),
@@ -59,7 +60,7 @@ class SceneSpecC(C.Structure):
                 ("n_materials", C.c_int32), ("n_textures", C.c_int32), ("materials", C.c_void_p),
                 ("textures", C.c_void_p), ("n_spectral_textures", C.c_int32), ("reserved", C.c_int32),
                 ("spectral_textures", C.c_void_p), ("camera", CameraSpec), ("bvh_seed", C.c_uint64),
-                ("bvh_rand_zero", C.c_int32), ("reserved2", C.c_int32)]
+                ("bvh_rand_zero", C.c_int32), ("bvh_builder", C.c_int32)]
 
 
 def f32(x):
@@ -71,8 +72,9 @@ def f32(x):
 class SceneSpec:
     """Accumulates primitives/materials/textures and produces an ``izpi_scene_spec``."""
 
-    def __init__(self, world_kind=WORLD_BVH4, bvh_seed=12345, bvh_rand_zero=False):
+    def __init__(self, world_kind=WORLD_BVH4, bvh_seed=12345, bvh_rand_zero=False, bvh_builder=BVH_REFERENCE):
         self.world_kind = world_kind
+        self.bvh_builder = bvh_builder
         self.bvh_seed = bvh_seed
         self.bvh_rand_zero = bvh_rand_zero
         self._prim_chunks: list[np.ndarray] = []
@@ -232,6 +234,7 @@ class SceneSpec:
                        n_materials=len(self.materials), n_textures=len(self.textures),
                        materials=C.addressof(mats), textures=C.addressof(texs),
                        n_spectral_textures=len(self.spectral_textures), spectral_textures=C.addressof(stex),
-                       camera=self.camera, bvh_seed=self.bvh_seed, bvh_rand_zero=int(self.bvh_rand_zero))
+                       camera=self.camera, bvh_seed=self.bvh_seed, bvh_rand_zero=int(self.bvh_rand_zero),
+                       bvh_builder=int(self.bvh_builder))
         s._keep = (prims, mats, texs, stex, self._keep)  # keep borrowed memory alive with the struct
         return s

@@ -1,0 +1,88 @@
+"""Device-side BVH4 build: build time vs the host restatement of hitable.NewBVH4, and closest-hit
+throughput / visit counts on the device-built tree vs the reference-shaped tree, on the config-2 mesh.
+
+    python scripts/bvh_device_bench.py [--rays 4194304] [--big]      (--big adds an 8M-triangle torus)
+Prints one JSON object per mesh."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from izpi_b200 import cuda, scenes  # noqa: E402
+from izpi_b200 import scene as S  # noqa: E402
+
+
+def tri_boxes(verts):
+    v = verts.reshape(-1, 3, 3)
+    mn, mx = v.min(1), v.max(1)
+    eps = np.maximum((mx - mn).max(1) * 1e-4, 1e-6)[:, None]
+    return np.concatenate([mn - eps, mx + eps], axis=1)
+
+
+def one(ctx, n_around, n_tube, n_rays):
+    verts, uvs = scenes.torus_mesh(n_around, n_tube)
+    boxes = tri_boxes(verts)
+    ctx.build_bvh4(boxes[:1000])  # warm (context, cub temp)
+    t0 = time.perf_counter()
+    nodes, perm = ctx.build_bvh4(boxes)
+    t_dev = time.perf_counter() - t0
+    lo, hi = verts.reshape(-1, 3).min(0), verts.reshape(-1, 3).max(0)
+    org, d = scenes.random_rays(n_rays, lo, hi)
+    out = {"triangles": len(verts), "device_build_s": t_dev, "device_nodes": int(len(nodes))}
+    res = {}
+    for name, builder in (("reference", S.BVH_REFERENCE), ("device_lbvh", S.BVH_DEVICE_LBVH)):
+        sc = S.SceneSpec(bvh_seed=12345, bvh_builder=builder)
+        sc.triangles(verts, sc.lambertian(sc.constant_texture((0.5, 0.5, 0.5))), uvs)
+        t0 = time.perf_counter()
+        hs = cuda.HostScene(sc)
+        t_scene = time.perf_counter() - t0
+        ctx.upload(hs)
+        ids, t, st = ctx.trace_closest(org, d, stats=True)
+        best = 1e9
+        # time the device entry point (rays resident in HBM), best of 3
+        import torch
+        d_org, d_dir = torch.from_numpy(org).cuda(), torch.from_numpy(d).cuda()
+        d_ids = torch.empty(n_rays, dtype=torch.int32, device="cuda")
+        d_t = torch.empty(n_rays, dtype=torch.float64, device="cuda")
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                ctx.trace_closest_device(n_rays, d_org.data_ptr(), d_dir.data_ptr(), d_ids.data_ptr(), d_t.data_ptr(), stream=stream.cuda_stream)
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ctx.trace_closest_device(n_rays, d_org.data_ptr(), d_dir.data_ptr(), d_ids.data_ptr(), d_t.data_ptr(), stream=stream.cuda_stream)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+        res[name] = (ids, t)
+        out[name] = {"scene_create_s": t_scene, "nodes": int(hs.bvh()[0].shape[0]), "nodes_per_ray": st["nodes"] / st["rays"],
+                     "prim_tests_per_ray": st["prims"] / st["rays"], "mrays_per_s": n_rays / best / 1e3, "kernel_ms": best}
+        del hs, sc
+    (ri, rt), (di, dt) = res["reference"], res["device_lbvh"]
+    out["t_bit_equal"] = bool(rt.tobytes() == dt.tobytes())
+    out["ids_equal_frac"] = float((ri == di).mean())
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=1 << 22)
+    ap.add_argument("--big", action="store_true")
+    a = ap.parse_args()
+    from izpi_b200.build import build
+    build()
+    ctx = cuda.Context(0)
+    print(json.dumps(one(ctx, 1000, 500, a.rays)), flush=True)
+    if a.big:
+        print(json.dumps(one(ctx, 2828, 1414, a.rays)), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
