@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libizpi_cuda.so")
 BUILD = os.path.join(HERE, "build")
 
 CU = ["device/context.cu", "device/trace.cu", "device/render.cu", "device/displace.cu", "device/bvh_build.cu"]
-CPP = ["host/error.cpp", "host/bvh4_builder.cpp", "host/host_scene.cpp"]
+CPP = ["host/error.cpp", "host/bvh4_builder.cpp", "host/host_scene.cpp", "host/proto_scene.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # --fmad=false: Go/amd64 never fuses multiply-add; bit-exact parity with the reference depends on it.
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread",

@@ -46,6 +46,11 @@ EXPORTS = [
     "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
     "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
     "izpi_host_tiles", "izpi_host_render",
+    # include/izpi_proto.h
+    "izpi_proto_scene_parse", "izpi_proto_scene_append_triangles", "izpi_proto_scene_to_scene", "izpi_proto_scene_spec",
+    "izpi_proto_scene_name", "izpi_proto_scene_colour_representation", "izpi_proto_scene_total_triangles",
+    "izpi_proto_scene_stream_triangles", "izpi_proto_scene_num_parsed_triangles", "izpi_proto_scene_background",
+    "izpi_proto_scene_num_images", "izpi_proto_scene_image_filename", "izpi_proto_scene_destroy",
 ]
 
 _lib = None
@@ -115,7 +120,8 @@ def tiles(size_x: int, size_y: int):
 class HostScene:
     """scene.Scene as built by the host runtime (izpi_host_scene_create)."""
 
-    def __init__(self, spec: SceneSpec, threads: int | None = None):
+    def __init__(self, spec, threads: int | None = None):
+        """spec: a scene.SceneSpec or a proto.ProtoScene (anything with to_c() -> izpi_scene_spec)."""
         self._spec = spec
         self._c = spec.to_c()
         h = C.c_void_p()

@@ -25,7 +25,7 @@ def _declared(header):
 
 
 def test_exports_match_headers():
-    declared = _declared("izpi_cuda.h") | _declared("izpi_host.h")
+    declared = _declared("izpi_cuda.h") | _declared("izpi_host.h") | _declared("izpi_proto.h")
     assert declared == set(cuda.EXPORTS)
     L = C.CDLL(cuda.LIB_PATH)
     for name in declared:
