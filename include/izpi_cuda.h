@@ -189,6 +189,13 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg);
  * NULL the rendered tiles' pixels are also written there (4*W*H doubles, Float64NRGBA layout,
  * reference row flip rgb.go:41). */
 int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* x0y0x1y1, double* canvas_rgba);
+/* worker.RenderTile (internal/worker/render.go:17-75; RenderTileRequest/Response, internal/proto/control/control.proto:75-89):
+ * renders ONE tile and returns what the worker streams back, row by row: (y1-y0+1) rows, row r = image row y0 + r (the
+ * worker does not flip; the leader places it at ny - pos_y, render/remote.go:63-69), each row strip_height*4*(x1-x0+1)
+ * doubles of which the first 4*(x1-x0+1) are {R,G,B,1} (spectral: CIE X,Y,Z) pixel means and the rest zeros, as the
+ * reference allocates them.  The Go worker wraps row r into RenderTileResponse{width, height: 1, pos_x: x0, pos_y: y0+r}.
+ * Also accumulates into the device canvas like izpi_render_tiles; a tile must be requested once per setup. */
+int izpi_render_tile_rows(izpi_ctx* ctx, uint32_t strip_height, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, double* rows);
 /* Device pointer of the context's canvas accumulator (4*W*H doubles: per-pixel SUMS over the
  * samples rendered so far, alpha = 1 where written) so that the host runtime can ncclReduce it. */
 int izpi_render_canvas_device(izpi_ctx* ctx, double** d_canvas);

@@ -497,7 +497,9 @@ __global__ void advance_kernel(Queues q, unsigned long long* host_visible_count)
 
 // ---- resolve ----------------------------------------------------------------------------------
 // canvas holds running per-pixel SUMS (rgb.go:30-37 adds sample after sample); the row is ny - y and
-// y == 0 falls outside the image (rgb.go:41; floatimage drops out-of-bounds Set calls).
+// y == 0 falls outside the image (rgb.go:41; floatimage drops out-of-bounds Set calls).  The device canvas has one
+// hidden row `height` that receives y == 0: the local path never copies it out, the worker path (izpi_render_tile_rows)
+// streams it like any other row, as worker.RenderTile does (worker/render.go:33-69).
 __global__ void resolve_kernel(RenderParams rp, const PathState* __restrict__ paths, const uint32_t* __restrict__ pixels,
                                int n_pixels, int s_count, double* canvas) {
   int pl = blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,7 +507,7 @@ __global__ void resolve_kernel(RenderParams rp, const PathState* __restrict__ pa
   uint32_t xy = pixels[pl];
   int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
   int row = rp.height - y;
-  if (row < 0 || row >= rp.height) return;
+  if (row < 0 || row > rp.height) return;
   double* px = canvas + ((size_t)row * rp.width + x) * 4;
   double a = px[0], b = px[1], c = px[2];
   const PathState* p = paths + (size_t)pl * s_count;
@@ -521,6 +523,22 @@ __global__ void mean_kernel(RenderParams rp, const double* __restrict__ sums, do
   if (rp.sampler != IZPI_SAMPLER_SPECTRAL) { a = a / (double)rp.spp; b = b / (double)rp.spp; c = c / (double)rp.spp; }
   else { double inv = 1.0 / (double)rp.spp; a = a * inv; b = b * inv; c = c * inv; }
   out[4 * i] = a; out[4 * i + 1] = b; out[4 * i + 2] = c; out[4 * i + 3] = sums[4 * i + 3];
+}
+
+// worker.RenderTile's reply rows (worker/render.go:33-69): row r = image row y0 + r (no flip), `stride` doubles per row of
+// which the first 4 * width are the pixel means (RGB: sum / spp, worker/render.go:86; spectral: sum * (1/spp),
+// render/spectral.go:99-103), alpha 1; the rest stays zero like the reference's make([]float64, stripSize).
+__global__ void tile_rows_kernel(RenderParams rp, const double* __restrict__ sums, int x0, int y0, int w, int h, long long stride,
+                                 double* __restrict__ rows) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)w * h) return;
+  int r = (int)(i / w), c = (int)(i % w);
+  const double* px = sums + ((size_t)(rp.height - (y0 + r)) * rp.width + (x0 + c)) * 4;
+  double a = px[0], b = px[1], d = px[2];
+  if (rp.sampler != IZPI_SAMPLER_SPECTRAL) { a = a / (double)rp.spp; b = b / (double)rp.spp; d = d / (double)rp.spp; }
+  else { double inv = 1.0 / (double)rp.spp; a = a * inv; b = b * inv; d = d * inv; }
+  double* o = rows + (size_t)r * stride + (size_t)c * 4;
+  o[0] = a; o[1] = b; o[2] = d; o[3] = 1.0;
 }
 
 // spectral.FireflyRejection (firefly_rejection.go:12-113): 3x3 neighbourhood of a SNAPSHOT of Y
@@ -801,13 +819,14 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
     rp.n_bg = cfg->n_bg; rp.bg_w = r->d_bg; rp.bg_v = r->d_bg + cfg->n_bg;
   }
   size_t n_px = (size_t)cfg->width * cfg->height;
-  if (n_px > r->canvas_capacity) {
+  const size_t n_px_hidden = n_px + (size_t)cfg->width;  // + the hidden row of y == 0 (resolve_kernel)
+  if (n_px_hidden > r->canvas_capacity) {
     cudaFree(r->d_canvas); cudaFree(r->d_out); cudaFree(r->d_snap);
     r->d_canvas = r->d_out = r->d_snap = nullptr; r->canvas_capacity = 0;
-    IZ_CUDA(cudaMalloc(&r->d_canvas, n_px * 32));
-    IZ_CUDA(cudaMalloc(&r->d_out, n_px * 32));
-    IZ_CUDA(cudaMalloc(&r->d_snap, n_px * 32));
-    r->canvas_capacity = n_px;
+    IZ_CUDA(cudaMalloc(&r->d_canvas, n_px_hidden * 32));
+    IZ_CUDA(cudaMalloc(&r->d_out, n_px_hidden * 32));
+    IZ_CUDA(cudaMalloc(&r->d_snap, n_px_hidden * 32));
+    r->canvas_capacity = n_px_hidden;
   }
   if (!r->allocated) {
     IZ_CUDA(cudaMalloc(&r->d_total_rays, sizeof(unsigned long long)));
@@ -829,7 +848,7 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
   }
   rc = sync_slots(r);
   if (rc != IZPI_OK) return rc;
-  IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px * 32, ctx->stream));
+  IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px_hidden * 32, ctx->stream));
   IZ_CUDA(cudaMemsetAsync(r->d_total_rays, 0, sizeof(unsigned long long), ctx->stream));
   IZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return IZPI_OK;
@@ -895,6 +914,32 @@ int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* tiles, dou
     if ((rc = sync_slots(r)) != IZPI_OK) return rc;
   }
   if (canvas_rgba) return canvas_to_host(ctx, r, canvas_rgba, false);
+  return IZPI_OK;
+}
+
+int izpi_render_tile_rows(izpi_ctx* ctx, uint32_t strip_height, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, double* rows) {
+  if (!ctx || !rows) { set_error("izpi_render_tile_rows: bad argument"); return IZPI_EINVAL; }
+  RenderState* r = ctx->render;
+  if (!r) { set_error("izpi_render_tile_rows: izpi_render_setup has not been called"); return IZPI_ESTATE; }
+  if (strip_height == 0) { set_error("izpi_render_tile_rows: strip_height 0 (the reference indexes an empty slice here)"); return IZPI_EINVAL; }
+  const uint32_t tile[4] = {x0, y0, x1, y1};
+  int rc = izpi_render_tiles(ctx, 1, tile, nullptr);  // validates the bounds
+  if (rc != IZPI_OK) return rc;
+  const int w = (int)(x1 - x0 + 1), h = (int)(y1 - y0 + 1);
+  const long long stride = (long long)strip_height * 4 * w;
+  double* d_rows = nullptr;
+  IZ_CUDA(cudaMalloc(&d_rows, (size_t)stride * h * 8));
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaMemsetAsync(d_rows, 0, (size_t)stride * h * 8, st);
+  if (e == cudaSuccess) {
+    rc = launch(ctx, st, tile_rows_kernel, dim3((unsigned)(((long long)w * h + 127) / 128)), dim3(128), 0, r->rp, r->d_canvas, (int)x0, (int)y0, w, h,
+                stride, d_rows);
+    if (rc == IZPI_OK) e = cudaMemcpyAsync(rows, d_rows, (size_t)stride * h * 8, cudaMemcpyDeviceToHost, st);
+    if (rc == IZPI_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  cudaFree(d_rows);
+  if (rc != IZPI_OK) return rc;
+  if (e != cudaSuccess) { set_error(std::string("izpi_render_tile_rows: ") + cudaGetErrorString(e)); return IZPI_ECUDA; }
   return IZPI_OK;
 }
 

@@ -41,7 +41,7 @@ class RenderConfig(C.Structure):
 # every symbol include/izpi_cuda.h and include/izpi_host.h declare (checked by tests/test_abi.py)
 EXPORTS = [
     "izpi_last_error", "izpi_version", "izpi_ctx_create", "izpi_ctx_destroy", "izpi_scene_upload",
-    "izpi_trace_closest", "izpi_trace_closest_device", "izpi_launch_count", "izpi_render_setup", "izpi_render_tiles",
+    "izpi_trace_closest", "izpi_trace_closest_device", "izpi_launch_count", "izpi_render_setup", "izpi_render_tiles", "izpi_render_tile_rows",
     "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_displace", "izpi_displace_fetch", "izpi_bvh4_build", "izpi_bvh4_build_fetch",
     "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
     "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
@@ -84,6 +84,7 @@ def lib():
     L.izpi_bvh4_build_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.izpi_render_setup.argtypes = [C.c_void_p, C.POINTER(RenderConfig)]
     L.izpi_render_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.izpi_render_tile_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     L.izpi_render_canvas_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.izpi_render_finish.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     L.izpi_host_scene_create.argtypes = [C.POINTER(SceneSpecC), C.c_int, C.POINTER(C.c_void_p)]
@@ -242,6 +243,27 @@ class Context:
         rays = C.c_uint64()
         check(lib().izpi_host_render(self._h, C.byref(cfg), tile_begin, tile_end, int(finish), canvas.ctypes.data, C.byref(rays)))
         return canvas, rays.value
+
+    # ---- worker.RenderSetup / RenderTile ------------------------------------------------------
+    def render_setup(self, width, height, spp, max_depth=50, sampler=SAMPLER_COLOUR, seed=1, background=(0.0, 0.0, 0.0),
+                     bg_wavelengths=None, bg_values=None):
+        """RenderSetupRequest (control.proto:56-68)."""
+        cfg = RenderConfig(width=width, height=height, spp=spp, max_depth=max_depth, sampler=sampler, sample_offset=0, sample_count=spp, seed=seed)
+        cfg.background[:] = [float(c) for c in background]
+        keep = []
+        if bg_wavelengths is not None and len(bg_wavelengths):
+            w = np.ascontiguousarray(bg_wavelengths, dtype=np.float64)
+            v = np.ascontiguousarray(bg_values, dtype=np.float64)
+            keep = [w, v]
+            cfg.bg_wavelengths, cfg.bg_values, cfg.n_bg = w.ctypes.data, v.ctypes.data, len(w)
+        check(lib().izpi_render_setup(self._h, C.byref(cfg)))
+        del keep
+
+    def render_tile_rows(self, x0, y0, x1, y1, strip_height=1):
+        """RenderTileRequest -> the rows of the RenderTileResponse stream: (y1-y0+1, strip_height*4*(x1-x0+1))."""
+        rows = np.zeros((y1 - y0 + 1, strip_height * 4 * (x1 - x0 + 1)), dtype=np.float64)
+        check(lib().izpi_render_tile_rows(self._h, strip_height, x0, y0, x1, y1, rows.ctypes.data))
+        return rows
 
     def canvas_device_ptr(self) -> int:
         p = C.c_void_p()

@@ -160,3 +160,27 @@ def test_aov_samplers_same_path(ctx, oracle_mod, sampler):
     for spec in (scenes.cornell_box(1.0), scenes.cornell_pbr_mesh(1.0, n_around=60, n_tube=40, tex_size=64)):
         img, ref, frac = _same_path(ctx, oracle_mod, spec, 40, 40, 4, sampler, min_close=0.995)
         assert np.abs(img[1:, :, :3]).max() > 0
+
+
+def test_worker_tile_rows(ctx):
+    """worker.RenderTile's wire shape (worker/render.go:17-75): rows in image order (no flip), strip_height padding, and the
+    y == 0 row that the local path drops.  Pixel values are the local render's (same RNG keys, same kernels)."""
+    spec = scenes.cornell_box(1.0)
+    ctx.upload(cuda.HostScene(spec))
+    w = h = 50  # common.Tiles -> 25 x 25 tiles
+    img, _ = ctx.render(w, h, 4, sampler=cuda.SAMPLER_COLOUR, seed=9)
+    ctx.render_setup(w, h, 4, sampler=cuda.SAMPLER_COLOUR, seed=9)
+    rows = ctx.render_tile_rows(25, 0, 49, 24, strip_height=1)
+    assert rows.shape == (25, 100)
+    for r in range(1, 25):  # image row y sits at canvas row ny - y (rgb.go:41, remote.go:63-69)
+        assert rows[r].tobytes() == img[h - r, 25:50].tobytes()
+    assert np.isfinite(rows[0]).all() and (rows[0].reshape(-1, 4)[:, 3] == 1).all() and rows[0].reshape(-1, 4)[:, :3].max() > 0
+    rows2 = ctx.render_tile_rows(0, 25, 24, 49, strip_height=3)
+    assert rows2.shape == (25, 300)
+    assert (rows2[:, 100:] == 0).all()  # make([]float64, stripSize): only the first row of the strip is filled
+    for r in range(25):
+        assert rows2[r, :100].tobytes() == img[h - (25 + r), 0:25].tobytes()
+    with pytest.raises(cuda.IzpiError):
+        ctx.render_tile_rows(0, 0, 24, 24, strip_height=0)
+    with pytest.raises(cuda.IzpiError):
+        ctx.render_tile_rows(0, 0, 50, 24)
