@@ -34,16 +34,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    if os.environ.get("IZPI_LIB_PATH") and out is None:
+        return os.environ["IZPI_LIB_PATH"]  # a prebuilt experiment variant is in use: leave it alone
+    if out is None and not force and not needs_build():
         return LIB
     os.makedirs(BUILD, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     log = []
+    extra = os.environ.get("IZPI_NVCC_DEFS", "").split()  # e.g. "-DIZPI_G4_MIN_BLOCKS=7" for occupancy experiments
     for src in CU + CPP:
         obj = os.path.join(BUILD, src.replace("/", "_") + ".o")
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-x", "cu" if src.endswith(".cu") else "c++", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *extra, "-x", "cu" if src.endswith(".cu") else "c++", "-c", os.path.join(CSRC, src), "-o", obj]
         if not src.endswith(".cu"):
             cmd = [nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread", "-x", "c++", "-c",
                    os.path.join(CSRC, src), "-o", obj]
@@ -53,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed on " + src)
         objs.append(obj)
-    r = subprocess.run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-Xcompiler", "-pthread"], capture_output=True, text=True)
+    r = subprocess.run([nvcc, *ARCH, "-shared", "-o", out or LIB, *objs, "-lcudart", "-Xcompiler", "-pthread"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
@@ -61,8 +64,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    outs = [a[len("--out="):] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=outs[0] if outs else None))

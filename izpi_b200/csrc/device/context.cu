@@ -143,6 +143,16 @@ int izpi_scene_upload(izpi_ctx* ctx, const izpi_scene_desc* d) {
         }
       }
     }
+    if (ok) {
+      // final form of a child record: {minx miny minz maxx | maxy maxz ref cnt} with ref = node index for an inner child and
+      // ~((first primitive << 2) | (count - 1)) for a (folded) leaf; an empty slot gets NaN bounds, which fail every
+      // comparison of the slab test, so the traversal needs no `ChildIndex == -1` branch (bvh4.go:108-110)
+      const float qnan = __builtin_nanf("");
+      for (Child& c : t) {
+        if (c.idx == -1) { c.mnx = c.mny = c.mnz = c.mxx = c.mxy = c.mxz = qnan; c.idx = 0; c.cnt = 0; }
+        else if (c.cnt > 0) c.idx = ~((c.idx << 2) | (c.cnt - 1));
+      }
+    }
     s.g4_ok = ok ? 1 : 0;
     s.root_is_leaf = (ok && pure_leaf(d->nodes[0])) ? 1 : 0;
     if (ok) {

@@ -31,7 +31,7 @@ struct DScene {
   int32_t g4_ok;                // nodes_t is usable (reference-shaped tree: leaves are own slot-0-only nodes)
   int32_t root_is_leaf, pad;
   const float4* nodes;          // 8 x float4 per BVH4Node, verbatim SoA layout, 128-B aligned
-  const float4* nodes_t;        // child-major copy: 4 x {minx miny minz maxx | maxy maxz idx cnt}, leaf-nodes folded in
+  const float4* nodes_t;        // child-major copy: 4 x {minx miny minz maxx | maxy maxz ref cnt}, leaf-nodes folded in, empty slots NaN (context.cu)
   const izpi_prim_rec* prims;   // 80-B records in world order, 16-B aligned
   const izpi_tri_attr* attrs;   // 128-B records, same index
   const izpi_xform* xforms;

@@ -26,51 +26,56 @@
 namespace izpi {
 
 constexpr int kG4Stack = 64;        // entries per ray (bvh4.go:71)
-constexpr int kG4Slab = kG4Stack + 7;  // int2 slots of shared memory per ray: the stack, the fp64 ray (6 doubles), 1 pad
+constexpr int kG4Slab = kG4Stack + 10;  // int2 slots of shared memory per ray: the stack, the fp64 ray (6 doubles), the fp32 ray (6 floats), 1 pad
 constexpr int kNodeStragglers = 4;  // default: leave the node phase when <= this many groups are still in it
 
 // Per-lane registers hold only what the node phase needs; the fp64 origin/direction (used by the primitive
 // tests alone) live in the ray's shared-memory slab behind its stack, which buys resident warps: the kernel is
 // latency-bound and its throughput is linear in them (scripts/sweep_blocks.sh).
 struct G4State {
-  float ox, oy, oz, ix, iy, iz;
   double tmax;
   int best;   // record index of the closest primitive so far
   int sp;     // stack pointer
-  int cur;    // >= 0: inner node to visit; kLeaf: leaf pending; kIdle: no ray
-  int leaf;   // pending leaf: (first primitive << 2) | (count - 1)
+  int cur;    // >= 0: inner node to visit; kIdle: no ray; <= kLeaf: a pending leaf, see g4_leaf_ref / g4_leaf_of
   bool fast;  // no NaN can arise in the slab test: FMNMX min/max equal the SSE selects
 };
 constexpr int kLeaf = -2, kIdle = -1;
+// a pending leaf L = (first primitive << 2) | (count - 1) >= 0 is kept in `cur` as kLeaf - L (one register for both)
+__device__ __forceinline__ int g4_leaf_ref(int leaf) { return kLeaf - leaf; }
+__device__ __forceinline__ int g4_leaf_of(int cur) { return kLeaf - cur; }
+__device__ __forceinline__ bool g4_in_leaf(int cur) { return cur <= kLeaf; }
 
 // stack entry: ref >= 0 inner node; ref < 0 leaf: ~ref = (first primitive << 2) | (count - 1)
 __device__ __forceinline__ void g4_begin(G4State& s, const DScene& sc, const DRay& r, double tmax, int2* slab, int j) {
+  const float ix = (float)(1.0 / r.d.x), iy = (float)(1.0 / r.d.y), iz = (float)(1.0 / r.d.z);  // bvh4.go:61-66
+  const float ox = (float)r.o.x, oy = (float)r.o.y, oz = (float)r.o.z;                            // bvh4.go:67
   if (j == 0) {
     double* rs = reinterpret_cast<double*>(slab + kG4Stack);
     rs[0] = r.o.x; rs[1] = r.o.y; rs[2] = r.o.z; rs[3] = r.d.x; rs[4] = r.d.y; rs[5] = r.d.z;
+    // the fp32 ray of the slab test is node-phase state only: it lives behind the fp64 ray and is reloaded at phase entry,
+    // so that it holds no registers during the (register-hungry) primitive tests
+    float* rf = reinterpret_cast<float*>(slab + kG4Stack + 6);
+    rf[0] = ox; rf[1] = oy; rf[2] = oz; rf[3] = ix; rf[4] = iy; rf[5] = iz;
   }
-  s.ix = (float)(1.0 / r.d.x); s.iy = (float)(1.0 / r.d.y); s.iz = (float)(1.0 / r.d.z);  // bvh4.go:61-66
-  s.ox = (float)r.o.x; s.oy = (float)r.o.y; s.oz = (float)r.o.z;                            // bvh4.go:67
   s.tmax = tmax; s.best = -1; s.sp = 0;
   s.cur = sc.n_nodes > 0 ? 0 : kIdle;
-  s.leaf = 0;
   // (bound - o) * inv is NaN only for 0 * Inf or Inf * 0: impossible when the origin is small enough for the
   // subtraction not to overflow and 1/d is finite and non-zero.  MINPS/MAXPS then agree with FMNMX (up to the
   // sign of zero, which no comparison below sees).
   const float big = 1e30f;
-  s.fast = fabsf(s.ox) < big && fabsf(s.oy) < big && fabsf(s.oz) < big && fabsf(s.ix) <= 3.0e38f && fabsf(s.iy) <= 3.0e38f &&
-           fabsf(s.iz) <= 3.0e38f && s.ix != 0.0f && s.iy != 0.0f && s.iz != 0.0f;
+  s.fast = fabsf(ox) < big && fabsf(oy) < big && fabsf(oz) < big && fabsf(ix) <= 3.0e38f && fabsf(iy) <= 3.0e38f &&
+           fabsf(iz) <= 3.0e38f && ix != 0.0f && iy != 0.0f && iz != 0.0f;
 }
 
 // Pop until something to do is found; leaves the ray idle when the stack is empty.
 template <bool COUNT>
-__device__ __forceinline__ void g4_pop(G4State& s, const int2* stack, uint32_t& n_nodes) {
+__device__ __forceinline__ void g4_pop(G4State& s, const DScene& sc, const int2* stack, int j, uint32_t& n_nodes) {
   while (s.sp > 0) {
     s.sp--;
     int2 e = stack[s.sp];
     if (e.x >= 0) { s.cur = e.x; return; }
     if (COUNT) n_nodes++;  // the reference loads the leaf node before its box test can fail
-    if ((float)s.tmax >= __int_as_float(e.y)) { s.cur = kLeaf; s.leaf = ~e.x; return; }
+    if ((float)s.tmax >= __int_as_float(e.y)) { s.cur = g4_leaf_ref(~e.x); return; }
   }
   s.cur = kIdle;
 }
@@ -80,11 +85,15 @@ template <bool COUNT>
 __device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2* stack, unsigned lane, int gshift, int j,
                                               uint32_t& n_nodes, int stragglers = kNodeStragglers) {
   const unsigned full = 0xffffffffu;
+  __syncwarp();  // the slab written by lane 0 of the group in g4_begin
+  const float4 ro = *reinterpret_cast<const float4*>(stack + kG4Stack + 6);
+  const float2 ri = *reinterpret_cast<const float2*>(stack + kG4Stack + 8);
+  const float ox = ro.x, oy = ro.y, oz = ro.z, ix = ro.w, iy = ri.x, iz = ri.y;
   for (;;) {
     const bool in_node = s.cur >= 0;
     const unsigned nm = __ballot_sync(full, in_node);
     if (nm == 0) break;
-    if (__popc(nm) <= 4 * stragglers && __any_sync(full, s.cur == kLeaf)) break;
+    if (__popc(nm) <= 4 * stragglers && __any_sync(full, g4_in_leaf(s.cur))) break;
     bool hit = false;
     float tmn = 0.0f;
     int ref = 0;
@@ -92,13 +101,13 @@ __device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2
       const float4* np = sc.nodes_t + (size_t)s.cur * 8 + 2 * j;
       const float4 a = __ldg(np);
       const float4 b = __ldg(np + 1);
-      const int idx = __float_as_int(b.z), cnt = __float_as_int(b.w);
+      ref = __float_as_int(b.z);  // inner child: node index; leaf child: ~((first primitive << 2) | (count - 1)), built at upload
       if (COUNT) n_nodes++;
       const float tmaxf = (float)s.tmax;  // float32(tMax) at node entry (bvh4.go:100)
       // one lane of RayAABB4_SIMD (bvh4_simd_amd64.go:52-101); tmn is its t_min, tmx its t_max
-      const float t0x = __fmul_rn(__fsub_rn(a.x, s.ox), s.ix), t1x = __fmul_rn(__fsub_rn(a.w, s.ox), s.ix);
-      const float t0y = __fmul_rn(__fsub_rn(a.y, s.oy), s.iy), t1y = __fmul_rn(__fsub_rn(b.x, s.oy), s.iy);
-      const float t0z = __fmul_rn(__fsub_rn(a.z, s.oz), s.iz), t1z = __fmul_rn(__fsub_rn(b.y, s.oz), s.iz);
+      const float t0x = __fmul_rn(__fsub_rn(a.x, ox), ix), t1x = __fmul_rn(__fsub_rn(a.w, ox), ix);
+      const float t0y = __fmul_rn(__fsub_rn(a.y, oy), iy), t1y = __fmul_rn(__fsub_rn(b.x, oy), iy);
+      const float t0z = __fmul_rn(__fsub_rn(a.z, oz), iz), t1z = __fmul_rn(__fsub_rn(b.y, oz), iz);
       float tmx;
       if (s.fast) {
         tmn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
@@ -108,15 +117,15 @@ __device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2
         tmn = sse_max(tmn, sse_min(t0y, t1y)); tmx = sse_min(tmx, sse_max(t0y, t1y));
         tmn = sse_max(tmn, sse_min(t0z, t1z)); tmx = sse_min(tmx, sse_max(t0z, t1z));
       }
-      hit = (tmx >= tmn) && (tmx >= 0.0f) && (tmaxf >= tmn) && (idx != -1);
-      ref = cnt > 0 ? ~((idx << 2) | (cnt - 1)) : idx;
+      // an empty slot (ChildIndex == -1, bvh4.go:108-110) carries NaN bounds in this copy: every comparison is false
+      hit = (tmx >= tmn) && (tmx >= 0.0f) && (tmaxf >= tmn);
     }
     const unsigned m = (__ballot_sync(full, hit) >> gshift) & 0xfu;
     const int first = m ? __ffs(m) - 1 : 0;
     const int nref = __shfl_sync(full, ref, (lane & ~3u) + first);
     if (in_node) {
       if (m == 0) {
-        g4_pop<COUNT>(s, stack, n_nodes);
+        g4_pop<COUNT>(s, sc, stack, j, n_nodes);
       } else {
         if (hit && j != first)  // later hit children are pushed in slot order (bvh4.go:141-145)
           stack[s.sp + __popc(m & ((1u << j) - 1u)) - 1] = make_int2(ref, __float_as_int(tmn));
@@ -125,7 +134,7 @@ __device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2
           s.cur = nref;  // first hit child is visited next (bvh4.go:137-140)
         } else {         // ... and when it is a leaf its box test repeats with the same tMax: it passes
           if (COUNT && !sc.root_is_leaf) n_nodes++;  // (a root that is itself the leaf-node was already counted)
-          s.cur = kLeaf; s.leaf = ~nref;
+          s.cur = g4_leaf_ref(~nref);
         }
       }
     }
@@ -159,9 +168,10 @@ template <bool COUNT, bool F32 = false>
 __device__ __forceinline__ void g4_leaf_phase(G4State& s, const DScene& sc, const int2* stack, unsigned lane, int gshift, int j,
                                               uint32_t& n_nodes, uint32_t& n_prims, double tmin) {
   const unsigned full = 0xffffffffu;
-  const bool in_leaf = s.cur == kLeaf;
+  const bool in_leaf = g4_in_leaf(s.cur);
   if (!__any_sync(full, in_leaf)) return;
-  const int start = s.leaf >> 2, cnt = (s.leaf & 3) + 1;
+  const int leaf = g4_leaf_of(s.cur);  // meaningful when in_leaf
+  const int start = leaf >> 2, cnt = (leaf & 3) + 1;
   bool ok = false, strict = false;
   double t = 0;
   if (in_leaf && j < cnt) {
@@ -194,7 +204,7 @@ __device__ __forceinline__ void g4_leaf_phase(G4State& s, const DScene& sc, cons
       }
     }
   }
-  if (in_leaf) g4_pop<COUNT>(s, stack, n_nodes);
+  if (in_leaf) g4_pop<COUNT>(s, sc, stack, j, n_nodes);
 }
 
 }  // namespace izpi

@@ -52,7 +52,7 @@ trace_kernel(const __grid_constant__ DScene sc, long long n, const double* __res
 // and the warp alternates between a node phase and a leaf phase (intersect_g4.cuh).
 constexpr int kChunk = 256;
 #ifndef IZPI_G4_MIN_BLOCKS
-#define IZPI_G4_MIN_BLOCKS 6
+#define IZPI_G4_MIN_BLOCKS 7
 #endif
 
 template <bool COUNT, bool F32>
@@ -71,15 +71,26 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
   int chunk = (n32 / (warps * 4) + 7) & ~7;  // rays per atomicAdd: shrinks for small batches (tail balance)
   chunk = chunk < 8 ? 8 : (chunk > kChunk ? kChunk : chunk);
   uint32_t n_nodes = 0, n_prims = 0;
-  int chunk_next = 0, chunk_end = 0;  // warp-uniform
-  bool exhausted = false;
+  // Cold state lives in shared memory so that it holds no registers across the traversal phases (the kernel is bound by
+  // resident warps): the ray index of a group in the pad slot of its slab, the warp's position in its ray chunk in
+  // the pad slot of the warp's first slab (.y of the same int2; only group 0's is used).
+  int* ray_slot = reinterpret_cast<int*>(stack + kG4Stack + 9);                                          // .x = ray index (-1: none)
+  int2* chunk_slot = g4_stack_smem + (size_t)((threadIdx.x & ~31u) >> 2) * kG4Slab + kG4Stack + 9;        // warp-wide
+  int* chunk_pos = reinterpret_cast<int*>(chunk_slot) + 1;                                               // .y of group 0's pad: next ray
+  int* chunk_lim = reinterpret_cast<int*>(chunk_slot + kG4Slab) + 1;                                     // .y of group 1's pad: chunk end (-1: exhausted)
+  if (j == 0) *ray_slot = -1;
+  if (lane == 0) { *chunk_pos = 0; *chunk_lim = 0; }
+  __syncwarp();
   G4State s;
   s.cur = kIdle;
-  int ray = -1;
   for (;;) {
     // ---- hand rays to idle groups
     unsigned idle = __ballot_sync(0xffffffffu, s.cur == kIdle);
     if (idle) {
+      int chunk_next = *chunk_pos, chunk_end = *chunk_lim;
+      bool exhausted = chunk_end < 0;
+      if (exhausted) chunk_end = chunk_next = 0;
+      __syncwarp();
       if (chunk_next >= chunk_end && !exhausted) {
         unsigned long long b = 0;
         if (lane == 0) b = atomicAdd(&counters[0], (unsigned long long)chunk);
@@ -90,7 +101,7 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
       int before = __popc(idle & ((1u << gshift) - 1u)) >> 2;  // idle groups ahead of mine
       int total = __popc(idle) >> 2;
       if (s.cur == kIdle && chunk_next + before < chunk_end) {
-        ray = chunk_next + before;
+        const int ray = chunk_next + before;
         const double* po = org + 3 * (size_t)ray;
         const double* pd = dir + 3 * (size_t)ray;
         DRay r;
@@ -98,22 +109,27 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
         r.d = mk(pd[0], pd[1], pd[2]);
         r.time = 0; r.lambda = 0;
         g4_begin(s, sc, r, tmax, stack, j);
-        if (s.cur == kIdle && j == 0) { ids[ray] = -1; ts[ray] = 0.0; }
+        if (j == 0) {
+          if (s.cur == kIdle) { ids[ray] = -1; ts[ray] = 0.0; }
+          else *ray_slot = ray;
+        }
       }
       int take = chunk_end - chunk_next;
       chunk_next += take < total ? take : total;
+      if (lane == 0) { *chunk_pos = chunk_next; *chunk_lim = exhausted ? -1 : chunk_end; }
       if (exhausted && __ballot_sync(0xffffffffu, s.cur == kIdle) == 0xffffffffu) break;
     }
     // ---- node phase, then leaf phase (both warp-uniform)
     g4_node_phase<COUNT>(s, sc, stack, lane, gshift, j, n_nodes, stragglers);
     g4_leaf_phase<COUNT, F32>(s, sc, stack, lane, gshift, j, n_nodes, n_prims, tmin);
     // ---- finished rays write their answer
-    if (s.cur == kIdle && ray >= 0) {
-      if (j == 0) {
+    if (s.cur == kIdle && j == 0) {
+      const int ray = *ray_slot;
+      if (ray >= 0) {
         ids[ray] = s.best >= 0 ? sc.prims[s.best].orig_id : -1;
         ts[ray] = s.best >= 0 ? s.tmax : 0.0;
+        *ray_slot = -1;
       }
-      ray = -1;
     }
   }
   if (COUNT && j == 0) {

@@ -14,7 +14,7 @@ import numpy as np
 from .scene import NODE_DTYPE, SceneSpec, SceneSpecC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libizpi_cuda.so")
+LIB_PATH = os.environ.get("IZPI_LIB_PATH") or os.path.join(_HERE, "libizpi_cuda.so")  # override: kernel experiments
 
 OK, EINVAL, ECUDA, ESTATE = 0, -1, -2, -3
 TRACE_EXACT, TRACE_FP32 = 0, 1
