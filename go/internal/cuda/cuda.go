@@ -153,3 +153,49 @@ func (c *Context) RenderFinish(pix []float64) (uint64, error) {
 	}
 	return uint64(rays), nil
 }
+
+// RenderTileRows is worker.RenderTile's body (internal/worker/render.go:17-75): it renders the tile and returns the rows
+// the worker streams back; row r is image row y0+r and becomes RenderTileResponse{Width: x1-x0+1, Height: 1, PosX: x0,
+// PosY: y0+r, Pixels: rows[r*stride:(r+1)*stride]} with stride = stripHeight*4*(x1-x0+1).
+func (c *Context) RenderTileRows(stripHeight, x0, y0, x1, y1 uint32) ([]float64, error) {
+	stride := int(stripHeight) * 4 * int(x1-x0+1)
+	rows := make([]float64, stride*int(y1-y0+1))
+	if rc := C.izpi_render_tile_rows(c.h, C.uint32_t(stripHeight), C.uint32_t(x0), C.uint32_t(y0), C.uint32_t(x1), C.uint32_t(y1),
+		(*C.double)(ptr(rows))); rc != 0 {
+		return nil, lastError("izpi_render_tile_rows", rc)
+	}
+	return rows, nil
+}
+
+// BuildBVH4 is the optional device-side replacement of hitable.NewBVH4 (internal/hitable/bvh4.go:517): boxes holds
+// min.xyz max.xyz of every hitable's BoundingBox(time0, time1).  It returns BVH4.Nodes in the reference's 128-byte layout
+// and the permutation with Primitives[i] = hitables[perm[i]]; package hitable wraps them into a *BVH4.
+func (c *Context) BuildBVH4(boxes []float64) ([]C.izpi_bvh4_node, []int32, error) {
+	n := len(boxes) / 6
+	var nn C.int32_t
+	if rc := C.izpi_bvh4_build(c.h, C.int32_t(n), (*C.double)(ptr(boxes)), &nn); rc != 0 {
+		return nil, nil, lastError("izpi_bvh4_build", rc)
+	}
+	nodes := make([]C.izpi_bvh4_node, int(nn))
+	perm := make([]int32, n)
+	if rc := C.izpi_bvh4_build_fetch(c.h, ptr(nodes), (*C.int32_t)(ptr(perm))); rc != 0 {
+		return nil, nil, lastError("izpi_bvh4_build_fetch", rc)
+	}
+	return nodes, perm, nil
+}
+
+// ApplyDisplacement is displacement.ApplyDisplacementMap (internal/displacement/displacement.go:145) on the device.
+// tris15: v0 v1 v2 u0 v0 u1 v1 u2 v2 per triangle; pix: the map as W*H*4 float64 RGBA (height in the blue channel).
+func (c *Context) ApplyDisplacement(tris15 []float64, materials []int32, w, h int, pix []float64, min, max float64) ([]float64, []int32, error) {
+	var nOut C.int64_t
+	if rc := C.izpi_displace(c.h, C.int64_t(len(materials)), (*C.double)(ptr(tris15)), (*C.int32_t)(ptr(materials)), C.int32_t(w), C.int32_t(h),
+		(*C.double)(ptr(pix)), C.double(min), C.double(max), 1, &nOut); rc != 0 {
+		return nil, nil, lastError("izpi_displace", rc)
+	}
+	out := make([]float64, 15*int(nOut))
+	om := make([]int32, int(nOut))
+	if rc := C.izpi_displace_fetch(c.h, (*C.double)(ptr(out)), (*C.int32_t)(ptr(om))); rc != 0 {
+		return nil, nil, lastError("izpi_displace_fetch", rc)
+	}
+	return out, om, nil
+}

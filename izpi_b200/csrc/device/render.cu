@@ -209,7 +209,7 @@ extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* pat
 // 8 paths per warp, queue indices drawn in chunks, finished groups replaced immediately.
 constexpr int kExtendChunk = 256;
 
-__global__ void __launch_bounds__(kThreads, 6)  // 80 registers: six resident blocks per SM (latency-bound kernel)
+__global__ void __launch_bounds__(kThreads, 7)  // 72 registers: seven resident blocks per SM (latency-bound kernel; 8 gains nothing, trace.cu)
 extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q, int stragglers) {
   extern __shared__ int2 g4_stack_smem[];
   const unsigned full = 0xffffffffu;
