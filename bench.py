@@ -139,6 +139,10 @@ def bench_render(ctx, cuda, scenes, world, rank, barrier, with_4k=True):
     if with_4k:  # the multi-GPU target of BASELINE: a 4K render, tile-sharded
         cases.append(("config 5 scene: 4K IBL + displacement-tessellated 11.5M-triangle mesh 3840x2160 at 16 spp (BASELINE: 1024 spp)",
                       lambda: scenes.ibl_tessellated_mesh(ctx, 3840 / 2160)[0], 3840, 2160, 16, cuda.SAMPLER_COLOUR))
+        # same frame over the optional device-built BVH4 (izpi_bvh4_build): same closest hits, better tree; reported separately
+        from izpi_b200 import scene as _S
+        cases.append(("config 5 scene, BVH4 built on the device (Morton LBVH instead of the reference's random-axis median split), 16 spp",
+                      lambda: scenes.ibl_tessellated_mesh(ctx, 3840 / 2160, bvh_builder=_S.BVH_DEVICE_LBVH)[0], 3840, 2160, 16, cuda.SAMPLER_COLOUR))
     for name, make, w, h, spp, sampler in cases:
         spec = make()
         ctx.upload(cuda.HostScene(spec, threads=max(1, (os.cpu_count() or 8) // world)))

@@ -262,7 +262,7 @@ def height_map(width: int = 4096, height: int = 2048):
 
 
 def ibl_tessellated_mesh(ctx, aspect: float = 3840 / 2160, n_around: int = 160, n_tube: int = 80, map_size=(5632, 2816),
-                         range_fraction: float = 0.9, env_size=(4096, 2048), bvh_seed: int = 12345):
+                         range_fraction: float = 0.9, env_size=(4096, 2048), bvh_seed: int = 12345, bvh_builder: int = S.BVH_REFERENCE):
     """Config 5 as BASELINE words it: image-based-lit scene with a DISPLACEMENT-TESSELLATED mesh.  A coarse torus
     (2*n_around*n_tube triangles, proto-style fp32 vertices) goes through displacement.ApplyDisplacementMap
     (run on the device, izpi_displace) with a smooth height map, one call per base triangle as transport.go:633-646
@@ -275,7 +275,7 @@ def ibl_tessellated_mesh(ctx, aspect: float = 3840 / 2160, n_around: int = 160, 
     rng = range_fraction * 2.0 / step
     verts, uvs = torus_mesh(n_around, n_tube, centre=(0.0, 0.0, 0.0), major=600.0, minor=240.0, amp=0.0)
     base = np.concatenate([verts.reshape(-1, 9), uvs.reshape(-1, 6)], axis=1)
-    sc = SceneSpec(world_kind=S.WORLD_BVH4, bvh_seed=bvh_seed)
+    sc = SceneSpec(world_kind=S.WORLD_BVH4, bvh_seed=bvh_seed, bvh_builder=bvh_builder)
     metal = sc.metal(f32((0.92, 0.86, 0.78)), f32(0.03))
     glass = sc.dielectric(f32(1.5))
     sky = sc.diffuse_light(sc.image_texture(sky_texture(*env_size)))

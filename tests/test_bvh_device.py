@@ -137,3 +137,27 @@ def test_mixed_primitives_same_closest_hit(ctx, oracle_mod):
     assert gt.tobytes() == ot.tobytes()
     assert (gi != oi).mean() <= 1e-4
     del rng
+
+
+def test_render_is_the_same_over_a_device_built_tree(ctx):
+    """The renderer only sees closest hits: a frame over the device-built BVH4 equals the frame over the reference-shaped
+    tree (same RNG keys, same hits).  Config-5 ingredients at test size: sky-dome sphere, glass sphere, metal mesh."""
+    imgs = []
+    for builder in (S.BVH_REFERENCE, S.BVH_DEVICE_LBVH):
+        sc = S.SceneSpec(bvh_seed=12345, bvh_builder=builder)
+        metal = sc.metal(S.f32((0.92, 0.86, 0.78)), S.f32(0.03))
+        glass = sc.dielectric(S.f32(1.5))
+        sky = sc.diffuse_light(sc.image_texture(scenes.sky_texture(64, 32)))
+        verts, uvs = scenes.torus_mesh(120, 60, centre=(0.0, 0.0, 0.0))
+        sc.triangles(verts, metal, uvs)
+        sc.sphere(S.f32((0.0, 22.0, 0.0)), float(S.f32(9.0)), glass)
+        sc.sphere(S.f32((0.0, 0.0, 0.0)), float(S.f32(500.0)), sky)
+        sc.prims["wrap"][-1] = S.WRAP_FLIP
+        sc.set_camera(S.f32((70, 45, 95)), S.f32((0, 2, 0)), S.f32((0, 1, 0)), S.f32(38), 1.0)
+        ctx.upload(cuda.HostScene(sc))
+        img, rays = ctx.render(64, 64, 8, max_depth=50, sampler=cuda.SAMPLER_COLOUR, seed=4)
+        imgs.append((img, rays))
+    (a, ra), (b, rb) = imgs
+    assert ra == rb
+    assert a.tobytes() == b.tobytes()
+    assert a[1:, :, :3].max() > 0

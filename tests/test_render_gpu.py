@@ -166,6 +166,8 @@ def test_worker_tile_rows(ctx):
     """worker.RenderTile's wire shape (worker/render.go:17-75): rows in image order (no flip), strip_height padding, and the
     y == 0 row that the local path drops.  Pixel values are the local render's (same RNG keys, same kernels)."""
     spec = scenes.cornell_box(1.0)
+    # a narrower field of view than scenes.go:119-155, so that the bottom image row (y == 0) looks into the box, not under it
+    spec.set_camera((278.0, 278.0, -800.0), (278, 278, 0), (0, 1, 0), 30.0, 1.0, 0.0, 10.0, 0.0, 1.0, 1.0)
     ctx.upload(cuda.HostScene(spec))
     w = h = 50  # common.Tiles -> 25 x 25 tiles
     img, _ = ctx.render(w, h, 4, sampler=cuda.SAMPLER_COLOUR, seed=9)
