@@ -252,10 +252,12 @@ int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double
   // The batch is cut into slices that alternate between two streams: while slice k is traversed, the rays of
   // slice k+1 arrive over PCIe and the answers of slice k-1 leave (the copies are truly asynchronous when the
   // caller's buffers are pinned; pageable buffers still work, just without the overlap).
-  const int64_t slice = 1 << 21;
+  // Slices grow from 2^18 to 2^21 rays: the first upload (nothing to overlap it with) stays short, later slices are large
+  // enough to keep the persistent kernel's tail small.
   cudaStream_t ss[2] = {ctx->stream, ctx->stream2};
   int k = 0;
-  for (int64_t b = 0; b < n; b += slice, k ^= 1) {
+  int64_t slice = 1 << 18;
+  for (int64_t b = 0; b < n; k ^= 1) {
     int64_t m = n - b < slice ? n - b : slice;
     cudaStream_t st = ss[k];
     IZ_CUDA(cudaMemcpyAsync(ctx->d_org + 3 * b, org + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, st));
@@ -265,6 +267,8 @@ int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double
     if (rc != IZPI_OK) return rc;
     IZ_CUDA(cudaMemcpyAsync(prim_id + b, ctx->d_ids + b, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     IZ_CUDA(cudaMemcpyAsync(t + b, ctx->d_t + b, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    b += m;
+    if (slice < (1 << 21)) slice <<= 1;
   }
   IZ_CUDA(cudaStreamSynchronize(ss[0]));
   IZ_CUDA(cudaStreamSynchronize(ss[1]));

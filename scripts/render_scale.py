@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--checksum", action="store_true")
     ap.add_argument("--tessellated", action="store_true", help="build the mesh with the displacement tessellator (izpi_displace) "
                     "instead of the analytically displaced torus")
+    ap.add_argument("--lbvh", action="store_true", help="BVH4 built on the device (izpi_bvh4_build) instead of the restated NewBVH4")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -43,7 +44,8 @@ def main():
     ctx = cuda.Context(local)
     t0 = time.perf_counter()
     if args.tessellated:
-        sc, n_tris = scenes.ibl_tessellated_mesh(ctx, args.width / args.height)
+        from izpi_b200 import scene as S
+        sc, n_tris = scenes.ibl_tessellated_mesh(ctx, args.width / args.height, bvh_builder=S.BVH_DEVICE_LBVH if args.lbvh else S.BVH_REFERENCE)
     else:
         sc, n_tris = scenes.ibl_displaced_mesh(args.width / args.height, args.around, args.tube), 2 * args.around * args.tube
     t_gen = time.perf_counter() - t0
@@ -70,7 +72,8 @@ def main():
         dt = float(tt.item())
     if rank == 0:
         n = args.width * args.height * args.spp
-        line = {"scene": "config 5: IBL + ~10M-triangle displaced mesh", "triangles": int(n_tris), "mesh": "displacement-tessellated (izpi_displace)" if args.tessellated else "analytic torus", "width": args.width,
+        line = {"scene": "config 5: IBL + ~10M-triangle displaced mesh", "triangles": int(n_tris), "mesh": "displacement-tessellated (izpi_displace)" if args.tessellated else "analytic torus",
+                "bvh": "device LBVH" if (args.lbvh and args.tessellated) else "reference (NewBVH4 restated)", "width": args.width,
                 "height": args.height, "spp": args.spp, "n_gpus": world, "msamples_per_s": n / dt / 1e6, "seconds": dt,
                 "mrays_per_s": r.num_rays / dt / 1e6, "rays_per_sample": r.num_rays / n, "scene_gen_s": t_gen,
                 "host_bvh_build_s": t_build, "upload_s": t_up, "mean_rgb": [float(x) for x in img[1:, :, :3].mean(axis=(0, 1))]}
