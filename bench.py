@@ -328,7 +328,7 @@ def main():
             "fp32_mode": fp32_info,
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (rank 0, bounded sample)
             threads = os.cpu_count() or 1
             n_cpu = 1 << 22
             v, ost, (oi, ot, oo, od) = cpu_baseline(sc, lo, hi, n_cpu, threads)
