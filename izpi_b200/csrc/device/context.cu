@@ -52,6 +52,8 @@ int izpi_ctx_create(int n_devices, const int* device_ids, izpi_ctx** out) {
   ctx->device = dev;
   { const char* e = getenv("IZPI_FORCE_SCALAR"); ctx->force_scalar = e && e[0] == '1'; }
   { const char* e = getenv("IZPI_NODE_STRAGGLERS"); if (e && e[0] >= '0' && e[0] <= '7') ctx->node_stragglers = e[0] - '0'; }
+  { const char* e = getenv("IZPI_PAIR_STRAGGLERS"); if (e) { int v = atoi(e); if (v >= 0 && v <= 15) ctx->pair_stragglers = v; } }
+  { const char* e = getenv("IZPI_TRACE_LANES"); if (e && (e[0] == '2' || e[0] == '4')) ctx->trace_lanes = e[0] - '0'; }
   cudaDeviceProp prop;
   IZ_CUDA(cudaGetDeviceProperties(&prop, dev));
   ctx->sm_count = prop.multiProcessorCount;
@@ -142,6 +144,29 @@ int izpi_scene_upload(izpi_ctx* ctx, const izpi_scene_desc* d) {
           for (int q = 0; q < 4; q++) if (ch.child_index[q] != -1 && ch.primitive_count[q] > 0) ok = false;  // mixed node
         }
       }
+    }
+    s.g4_need = 64;
+    if (ok) {
+      // Stack entries a ray can need in this tree: visiting a node with k valid children leaves at most k-1 entries below
+      // the child being visited (bvh4.go:137-160; folded leaves are pushed like nodes).  When every child index exceeds its
+      // parent's (pre-order numbering: NewBVH4 and the device build) one reverse sweep gives the bound; otherwise the
+      // reference's fixed 64 stands.
+      std::vector<int> need((size_t)nn, 0);
+      bool ordered = true;
+      for (int i = nn - 1; i >= 0 && ordered; i--) {
+        int k = 0, deepest = 0;
+        for (int q = 0; q < 4; q++) {
+          const Child& c = t[(size_t)i * 4 + q];
+          if (c.idx == -1) continue;
+          k++;
+          if (c.cnt == 0) {
+            if (c.idx <= i) { ordered = false; break; }
+            if (need[c.idx] > deepest) deepest = need[c.idx];
+          }
+        }
+        need[i] = k > 0 ? (k - 1) + deepest : 0;
+      }
+      s.g4_need = ordered && need[0] < 64 ? need[0] : 64;
     }
     if (ok) {
       // final form of a child record: {minx miny minz maxx | maxy maxz ref cnt} with ref = node index for an inner child and

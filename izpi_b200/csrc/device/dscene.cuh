@@ -29,7 +29,8 @@ struct DSpectralTexture {  // texture.SpectralConstant
 struct DScene {
   int32_t world_kind, n_nodes, n_prims, n_xforms, n_lights, n_materials, dielectric_has_world;
   int32_t g4_ok;                // nodes_t is usable (reference-shaped tree: leaves are own slot-0-only nodes)
-  int32_t root_is_leaf, pad;
+  int32_t root_is_leaf;
+  int32_t g4_need;              // most stack entries a ray can need in THIS tree (<= 64, bvh4.go:71); picks the slab size of the 2-lane kernel
   const float4* nodes;          // 8 x float4 per BVH4Node, verbatim SoA layout, 128-B aligned
   const float4* nodes_t;        // child-major copy: 4 x {minx miny minz maxx | maxy maxz ref cnt}, leaf-nodes folded in, empty slots NaN (context.cu)
   const izpi_prim_rec* prims;   // 80-B records in world order, 16-B aligned
@@ -62,6 +63,8 @@ struct izpi_ctx {
   cudaStream_t stream2 = nullptr;  // second lane of the copy/compute pipeline of izpi_trace_closest
   bool has_scene = false;
   int node_stragglers = 4;    // IZPI_NODE_STRAGGLERS: node-phase exit threshold of the 4-lanes-per-ray kernels
+  int pair_stragglers = 6;    // IZPI_PAIR_STRAGGLERS: the same for the 2-lanes-per-ray kernel (pairs)
+  int trace_lanes = 2;        // IZPI_TRACE_LANES=2|4: lanes per ray of izpi_trace_closest
   bool force_scalar = false;  // IZPI_FORCE_SCALAR=1: thread-per-ray traversal even for reference-shaped trees
   izpi::DScene scene{};
   std::vector<void*> scene_allocs;  // freed on re-upload / destroy

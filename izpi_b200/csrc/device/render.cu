@@ -14,7 +14,7 @@
 #include <algorithm>
 #include <cstring>
 
-#include "intersect_g4.cuh"
+#include "intersect_g2.cuh"
 #include "shade.cuh"
 
 using namespace izpi;
@@ -260,6 +260,80 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
     }
     g4_node_phase<false>(s, sc, stack, lane, gshift, j, nn, stragglers);
     g4_leaf_phase<false>(s, sc, stack, lane, gshift, j, nn, np, 0.001);
+    const bool done = s.cur == kIdle && pi >= 0;
+    if (__any_sync(full, done)) {
+      bool hit = false;
+      int cls = 0;
+      if (done && j == 0) {
+        PathState& p = paths[pi];
+        if (s.best < 0) {
+          finish_path(rp, p, mk(p.ax, p.ay, p.az) + hadamard(mk(p.bx, p.by, p.bz), background_term(rp, p.lambda)));
+        } else {
+          p.hit_rec = s.best; p.hit_t = s.tmax;
+          hit = true;
+          cls = sc.materials[tag_material(sc.prims[s.best].tag)].type;
+        }
+      }
+      push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + 2);
+      if (done) pi = -1;
+    }
+  }
+  if (traced) atomicAdd(&q.counters[8], (unsigned long long)traced);
+}
+
+
+// The same stage with two lanes per path (intersect_g2.cuh): 16 paths per warp.  Used when the tree's worst-case stack fits
+// the kG2Stack-entry slab (launch_cfg); trace.cu explains the trade.
+__global__ void __launch_bounds__(kThreads, 6)
+extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q, int stragglers) {
+  extern __shared__ int2 g4_stack_smem[];
+  constexpr int kSlots = G2Slab<kG2Stack>::kSlots;
+  const unsigned full = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const int j = lane & 1, pshift = (int)(lane & ~1u);
+  int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 1) * kSlots;
+  const int n = (int)q.counters[0];  // live paths of this bounce (a batch holds < 2^31 paths)
+  const int warps = (int)gridDim.x * (kThreads / 32);
+  int chunk = (n / (warps * 4) + 15) & ~15;
+  chunk = chunk < 16 ? 16 : (chunk > kExtendChunk ? kExtendChunk : chunk);
+  uint32_t nn = 0, np = 0;
+  unsigned traced = 0;
+  int chunk_next = 0, chunk_end = 0;
+  bool exhausted = false;
+  G4State s;
+  s.cur = kIdle;
+  int32_t pi = -1;
+  for (;;) {
+    unsigned idle = __ballot_sync(full, s.cur == kIdle);
+    if (idle) {
+      if (chunk_next >= chunk_end && !exhausted) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(&q.counters[7], (unsigned long long)chunk);
+        b = __shfl_sync(full, b, 0);
+        if (b >= (unsigned long long)n) { exhausted = true; chunk_next = chunk_end = 0; }
+        else { chunk_next = (int)b; chunk_end = (int)b + chunk < n ? (int)b + chunk : n; }
+      }
+      int before = __popc(idle & ((1u << pshift) - 1u)) >> 1, total = __popc(idle) >> 1;
+      if (s.cur == kIdle && chunk_next + before < chunk_end) {
+        pi = q.cur[chunk_next + before];
+        PathState& p = paths[pi];
+        if (p.depth >= rp.max_depth && rp.sampler <= IZPI_SAMPLER_SPECTRAL) {  // colour.go:34-36 / spectral.go:48-51
+          if (j == 0) {
+            d3 term = rp.sampler == IZPI_SAMPLER_COLOUR ? mk(0, 0, 1.0) : background_term(rp, p.lambda);
+            finish_path(rp, p, mk(p.ax, p.ay, p.az) + hadamard(mk(p.bx, p.by, p.bz), term));
+          }
+          pi = -1;
+        } else {
+          if (j == 0) traced++;  // atomic.AddUint64(numRays, 1) (colour.go:38)
+          g2_begin<kG2Stack>(s, sc, path_ray(p), DBL_MAX, stack, j);
+        }
+      }
+      int take = chunk_end - chunk_next;
+      chunk_next += take < total ? take : total;
+      if (exhausted && __ballot_sync(full, s.cur == kIdle && pi < 0) == full) break;
+    }
+    g2_node_phase<false, kG2Stack>(s, sc, stack, pshift, j, nn, stragglers);
+    g2_leaf_phase<false, false, kG2Stack>(s, sc, stack, pshift, j, nn, np, 0.001);
     const bool done = s.cur == kIdle && pi >= 0;
     if (__any_sync(full, done)) {
       bool hit = false;
@@ -662,25 +736,30 @@ int launch(izpi_ctx* ctx, cudaStream_t st, K kern, dim3 grid, dim3 block, size_t
 }
 
 struct LaunchCfg {
-  bool use_g4;
-  size_t smem, smem4;
-  int ext_blocks, ext4_blocks;
+  bool use_g4, use_g2;
+  size_t smem, smem4, smem2;
+  int ext_blocks, ext4_blocks, ext2_blocks;
 };
 
 int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
   lc.smem = (size_t)kStackDepth * kThreads * sizeof(int32_t);
   lc.smem4 = (size_t)(kThreads / 4) * kG4Slab * sizeof(int2);
-  static thread_local int ext_blocks = 0, ext4_blocks = 0;
+  lc.smem2 = (size_t)(kThreads / 2) * G2Slab<kG2Stack>::kSlots * sizeof(int2);
+  static thread_local int ext_blocks = 0, ext4_blocks = 0, ext2_blocks = 0;
   if (!ext_blocks) {
+    IZ_CUDA(cudaFuncSetAttribute(extend_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem2));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext2_blocks, extend_g2_kernel, kThreads, lc.smem2));
+    if (ext2_blocks < 1) ext2_blocks = 1;
     IZ_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_blocks, extend_kernel, kThreads, lc.smem));
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext4_blocks, extend_g4_kernel, kThreads, lc.smem4));
     if (ext_blocks < 1) ext_blocks = 1;
     if (ext4_blocks < 1) ext4_blocks = 1;
   }
-  lc.ext_blocks = ext_blocks; lc.ext4_blocks = ext4_blocks;
+  lc.ext_blocks = ext_blocks; lc.ext4_blocks = ext4_blocks; lc.ext2_blocks = ext2_blocks;
   // tiny trees (config 4 has 22 primitives) stay cache-resident and coherent: the thread-per-ray stage wins there
   lc.use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= 64;
+  lc.use_g2 = lc.use_g4 && ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2Stack;
   return IZPI_OK;
 }
 
@@ -717,7 +796,12 @@ int batch_step(izpi_ctx* ctx, RenderState* r, BatchSlot& s, const LaunchCfg& lc)
   if (s.live == 0 || s.bounce > r->rp.max_depth || s.bounce >= kMaxBounces) { s.drained = true; return IZPI_OK; }
   int rc;
   long long want = ((long long)s.live + kThreads - 1) / kThreads;
-  if (lc.use_g4) {
+  if (lc.use_g2) {
+    long long want2 = ((long long)s.live + (kThreads / 2) - 1) / (kThreads / 2);
+    int eg2 = (int)std::max<long long>(1, std::min<long long>(want2, (long long)sm * lc.ext2_blocks));
+    if ((rc = launch(ctx, st, extend_g2_kernel, dim3(eg2), dim3(kThreads), lc.smem2, ctx->scene, r->rp, s.d_paths, s.q,
+                     ctx->pair_stragglers)) != IZPI_OK) return rc;
+  } else if (lc.use_g4) {
     long long want4 = ((long long)s.live + (kThreads / 4) - 1) / (kThreads / 4);
     int eg4 = (int)std::max<long long>(1, std::min<long long>(want4, (long long)sm * lc.ext4_blocks));
     if ((rc = launch(ctx, st, extend_g4_kernel, dim3(eg4), dim3(kThreads), lc.smem4, ctx->scene, r->rp, s.d_paths, s.q,

@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "intersect_g4.cuh"
+#include "intersect_g2.cuh"
 
 using namespace izpi;
 
@@ -139,6 +139,114 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
   if (COUNT && j != 0) atomicAdd(&counters[2], (unsigned long long)n_prims);
 }
 
+
+// ---- 2 lanes per ray --------------------------------------------------------------------------
+// Sixteen ray slots per warp (intersect_g2.cuh); same queue, same replacement scheme as the 4-lane kernel.
+#ifndef IZPI_G2_MIN_BLOCKS
+#define IZPI_G2_MIN_BLOCKS 6
+#endif
+
+template <bool COUNT, bool F32, int STACK>
+__global__ void __launch_bounds__(kTraceThreads, IZPI_G2_MIN_BLOCKS)
+trace_g2_kernel(const __grid_constant__ DScene sc, long long n, const double* __restrict__ org,
+                const double* __restrict__ dir, double tmin, double tmax, int32_t* __restrict__ ids,
+                double* __restrict__ ts, unsigned long long* counters, int stragglers) {
+  extern __shared__ int2 g4_stack_smem[];  // [rays per block][STACK + 10]: one private slab per ray
+  constexpr int kSlots = G2Slab<STACK>::kSlots;
+  const unsigned lane = threadIdx.x & 31u;
+  const int j = lane & 1, pshift = (int)(lane & ~1u);
+  int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 1) * kSlots;
+  const int n32 = (int)n;
+  const int warps = (int)gridDim.x * (kTraceThreads / 32);
+  int chunk = (n32 / (warps * 4) + 15) & ~15;  // rays per atomicAdd: shrinks for small batches (tail balance)
+  chunk = chunk < 16 ? 16 : (chunk > kChunk ? kChunk : chunk);
+  uint32_t n_nodes = 0, n_prims = 0;
+  // cold state in shared memory (see trace_g4_kernel): ray index in the pad slot of the pair's slab, the warp's chunk cursor
+  // in the pad slots of its first two slabs
+  int* ray_slot = reinterpret_cast<int*>(stack + STACK + 9);
+  int2* chunk_slot = g4_stack_smem + (size_t)((threadIdx.x & ~31u) >> 1) * kSlots + STACK + 9;
+  int* chunk_pos = reinterpret_cast<int*>(chunk_slot) + 1;
+  int* chunk_lim = reinterpret_cast<int*>(chunk_slot + kSlots) + 1;
+  if (j == 0) *ray_slot = -1;
+  if (lane == 0) { *chunk_pos = 0; *chunk_lim = 0; }
+  __syncwarp();
+  G4State s;
+  s.cur = kIdle;
+  for (;;) {
+    unsigned idle = __ballot_sync(0xffffffffu, s.cur == kIdle);
+    if (idle) {
+      int chunk_next = *chunk_pos, chunk_end = *chunk_lim;
+      bool exhausted = chunk_end < 0;
+      if (exhausted) chunk_end = chunk_next = 0;
+      __syncwarp();
+      if (chunk_next >= chunk_end && !exhausted) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(&counters[0], (unsigned long long)chunk);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned long long)n32) { exhausted = true; chunk_next = chunk_end = 0; }
+        else { chunk_next = (int)b; chunk_end = (int)b + chunk < n32 ? (int)b + chunk : n32; }
+      }
+      int before = __popc(idle & ((1u << pshift) - 1u)) >> 1;  // idle pairs ahead of mine
+      int total = __popc(idle) >> 1;
+      if (s.cur == kIdle && chunk_next + before < chunk_end) {
+        const int ray = chunk_next + before;
+        const double* po = org + 3 * (size_t)ray;
+        const double* pd = dir + 3 * (size_t)ray;
+        DRay r;
+        r.o = mk(po[0], po[1], po[2]);
+        r.d = mk(pd[0], pd[1], pd[2]);
+        r.time = 0; r.lambda = 0;
+        g2_begin<STACK>(s, sc, r, tmax, stack, j);
+        if (j == 0) {
+          if (s.cur == kIdle) { ids[ray] = -1; ts[ray] = 0.0; }
+          else *ray_slot = ray;
+        }
+      }
+      int take = chunk_end - chunk_next;
+      chunk_next += take < total ? take : total;
+      if (lane == 0) { *chunk_pos = chunk_next; *chunk_lim = exhausted ? -1 : chunk_end; }
+      if (exhausted && __ballot_sync(0xffffffffu, s.cur == kIdle) == 0xffffffffu) break;
+    }
+    g2_node_phase<COUNT, STACK>(s, sc, stack, pshift, j, n_nodes, stragglers);
+    g2_leaf_phase<COUNT, F32, STACK>(s, sc, stack, pshift, j, n_nodes, n_prims, tmin);
+    if (s.cur == kIdle && j == 0) {
+      const int ray = *ray_slot;
+      if (ray >= 0) {
+        ids[ray] = s.best >= 0 ? sc.prims[s.best].orig_id : -1;
+        ts[ray] = s.best >= 0 ? s.tmax : 0.0;
+        *ray_slot = -1;
+      }
+    }
+  }
+  if (COUNT && j == 0) atomicAdd(&counters[1], (unsigned long long)n_nodes);
+  if (COUNT) atomicAdd(&counters[2], (unsigned long long)n_prims);
+}
+
+template <int STACK>
+int launch_g2(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir, double tmin, double tmax, int mode, int32_t* d_ids,
+              double* d_t, cudaStream_t st, bool count, unsigned long long* counters) {
+  const size_t smem = (size_t)(kTraceThreads / 2) * G2Slab<STACK>::kSlots * sizeof(int2);
+  auto k = mode == IZPI_TRACE_FP32 ? trace_g2_kernel<false, true, STACK> : (count ? trace_g2_kernel<true, false, STACK> : trace_g2_kernel<false, false, STACK>);
+  static thread_local int bps = 0;
+  if (!bps) {
+    IZ_CUDA(cudaFuncSetAttribute(trace_g2_kernel<false, false, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IZ_CUDA(cudaFuncSetAttribute(trace_g2_kernel<true, false, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IZ_CUDA(cudaFuncSetAttribute(trace_g2_kernel<false, true, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, trace_g2_kernel<false, false, STACK>, kTraceThreads, smem));
+    if (bps < 1) bps = 1;
+  }
+  int use_bps = bps;
+  if (const char* e = getenv("IZPI_TRACE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < use_bps) use_bps = v; }
+  long long want = (n + (kTraceThreads / 2) - 1) / (kTraceThreads / 2);
+  long long grid = (long long)ctx->sm_count * use_bps;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  k<<<(unsigned)grid, kTraceThreads, smem, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, counters, ctx->pair_stragglers);
+  IZ_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return IZPI_OK;
+}
+
 // Diagnostic: the 4-wide slab test alone, so the reference's golden masks can be replayed on the device.
 __global__ void box4_kernel(int n, const float* __restrict__ org, const float* __restrict__ inv,
                             const float* __restrict__ bounds, const float* __restrict__ tmax, uint8_t* __restrict__ masks) {
@@ -160,6 +268,15 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
   }
   if (n > (1ll << 30)) { set_error("izpi_trace_closest: at most 2^30 rays per launch; split the batch"); return IZPI_EINVAL; }
   IZ_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), st));
+  // Two lanes per ray (16 rays per warp) when the tree's worst-case stack fits the kG2Stack-entry slab (six resident
+  // blocks x 64 rays x 400 B of shared memory); with the reference's full 64 entries only five blocks would fit, and the
+  // 4-lane kernel (8 rays per warp, 7 blocks) is faster than that.  NewBVH4 trees are balanced -- three entries per level
+  // of inner nodes: 27 for the 1 M-triangle mesh, 33 for 11.5 M -- so they fit; a tree that does not is still traced
+  // exactly, by the 4-lane kernel.
+  if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && (!ctx->force_scalar || mode == IZPI_TRACE_FP32) &&
+      ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2Stack) {
+    return launch_g2<kG2Stack>(ctx, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, st, count, counters);
+  }
   if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && (!ctx->force_scalar || mode == IZPI_TRACE_FP32)) {
     size_t smem4 = (size_t)(kTraceThreads / 4) * kG4Slab * sizeof(int2);
     auto k4 = mode == IZPI_TRACE_FP32 ? trace_g4_kernel<false, true> : (count ? trace_g4_kernel<true, false> : trace_g4_kernel<false, false>);
