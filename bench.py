@@ -33,12 +33,12 @@ WORKLOAD = "closest-hit: 1M-triangle displaced torus (BVH4, LCG seed 12345), 16,
 def ncu_traffic(n_rays):
     """DRAM bytes per launch of the headline kernel from the committed `ncu --set full` capture (profiles/), scaled to the
     launch size when it differs from the captured one.  None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r01_trace_g4_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01_trace_traffic.json")
     try:
         t = json.load(open(p))
-        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (n_rays / t["rays_per_launch"])
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (n_rays / t["rays_per_launch"]), t["kernel"]
     except Exception:
-        return None
+        return None, "trace_g2_kernel<false,false,40>"
 
 
 def peaks():
@@ -320,7 +320,7 @@ def main():
                        "nodes_per_ray": nodes_per_ray, "prim_tests_per_ray": prims_per_ray,
                        "algorithmic_bytes_per_ray": bytes_per_ray},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": ncu_traffic(n), "kernel": "trace_g4_kernel<false,false>", "kernel_ms": kernel_ms, "peak_source": peak_src},
+                         "traffic": ncu_traffic(n)[0], "kernel": ncu_traffic(n)[1], "kernel_ms": kernel_ms, "peak_source": peak_src},
             "e2e": {"value": world * n * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 48,
                     "d2h_bytes_per_step": n * 12},
             "gpu_launches": int(launches),
