@@ -38,7 +38,7 @@ def ncu_traffic(n_rays):
         t = json.load(open(p))
         return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (n_rays / t["rays_per_launch"]), t["kernel"]
     except Exception:
-        return None, "trace_g2_kernel<false,false,40>"
+        return None, "trace_g2_kernel<false,false,48>"
 
 
 def peaks():

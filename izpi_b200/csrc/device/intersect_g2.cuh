@@ -16,7 +16,10 @@
 
 namespace izpi {
 
-constexpr int kG2Stack = 40;      // stack entries of the 2-lane kernel's slab; deeper trees use the 4-lane kernel (64 entries)
+#ifndef IZPI_G2_STACK
+#define IZPI_G2_STACK 48  // measured on config 2: 40 -> 680, 48 -> 678, 56 -> 668 Mrays/s; 64 would leave room for 5 blocks only
+#endif
+constexpr int kG2Stack = IZPI_G2_STACK;      // stack entries of the 2-lane kernel's slab; deeper trees use the 4-lane kernel (64 entries)
 constexpr int kG2Stragglers = 6;  // leave the node phase when <= this many PAIRS are still in it while leaves are pending
 
 template <int STACK>

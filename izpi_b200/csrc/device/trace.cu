@@ -269,7 +269,7 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
   if (n > (1ll << 30)) { set_error("izpi_trace_closest: at most 2^30 rays per launch; split the batch"); return IZPI_EINVAL; }
   IZ_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), st));
   // Two lanes per ray (16 rays per warp) when the tree's worst-case stack fits the kG2Stack-entry slab (six resident
-  // blocks x 64 rays x 400 B of shared memory); with the reference's full 64 entries only five blocks would fit, and the
+  // blocks x 64 rays x 464 B of shared memory); with the reference's full 64 entries only five blocks would fit, and the
   // 4-lane kernel (8 rays per warp, 7 blocks) is faster than that.  NewBVH4 trees are balanced -- three entries per level
   // of inner nodes: 27 for the 1 M-triangle mesh, 33 for 11.5 M -- so they fit; a tree that does not is still traced
   // exactly, by the 4-lane kernel.

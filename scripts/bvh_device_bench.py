@@ -24,6 +24,22 @@ def tri_boxes(verts):
     return np.concatenate([mn - eps, mx + eps], axis=1)
 
 
+def stack_need(nodes):
+    """Worst-case traversal stack use of a tree (children are numbered after their parents): k-1 entries below the child
+    being visited, leaf-nodes fold into their parent's slot (csrc/device/context.cu)."""
+    ci, pc = nodes["child_index"], nodes["primitive_count"]
+    n = len(nodes)
+    leafnode = pc[:, 0] > 0
+    need = np.zeros(n, dtype=np.int32)
+    for i in range(n - 1, -1, -1):
+        if leafnode[i]:
+            continue
+        kids = ci[i][ci[i] != -1]
+        inner = kids[~leafnode[kids]]
+        need[i] = len(kids) - 1 + (need[inner].max() if len(inner) else 0)
+    return int(need[0])
+
+
 def one(ctx, n_around, n_tube, n_rays):
     verts, uvs = scenes.torus_mesh(n_around, n_tube)
     boxes = tri_boxes(verts)
@@ -61,7 +77,7 @@ def one(ctx, n_around, n_tube, n_rays):
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))
         res[name] = (ids, t)
-        out[name] = {"scene_create_s": t_scene, "nodes": int(hs.bvh()[0].shape[0]), "nodes_per_ray": st["nodes"] / st["rays"],
+        out[name] = {"scene_create_s": t_scene, "nodes": int(hs.bvh()[0].shape[0]), "stack_need": stack_need(hs.bvh()[0]), "nodes_per_ray": st["nodes"] / st["rays"],
                      "prim_tests_per_ray": st["prims"] / st["rays"], "mrays_per_s": n_rays / best / 1e3, "kernel_ms": best}
         del hs, sc
     (ri, rt), (di, dt) = res["reference"], res["device_lbvh"]

@@ -188,3 +188,35 @@ def test_fp32_mode_agrees_closely(ctx, oracle_mod):
     ctx.upload(cuda.HostScene(scenes.cornell_box()))
     with pytest.raises(cuda.IzpiError):
         ctx.trace_closest(org[:8], d[:8], mode=cuda.TRACE_FP32)
+
+
+def test_lane_layouts_agree(oracle_mod, monkeypatch):
+    """The 2-lanes-per-ray kernel (default when the tree's stack bound fits its slab) and the 4-lanes-per-ray kernel (deep
+    trees, IZPI_TRACE_LANES=4) follow the same traversal: identical answers AND identical visit / test counts, on a ragged
+    batch size that leaves pairs and groups idle at the tail."""
+    verts, uvs = scenes.torus_mesh(200, 120)
+    sc = S.SceneSpec(bvh_seed=12345)
+    sc.triangles(verts, sc.lambertian(sc.constant_texture((0.5, 0.5, 0.5))), uvs)
+    r = np.random.default_rng(1)
+    for _ in range(50):
+        sc.sphere(r.uniform(20, 80, 3), r.uniform(0.5, 3.0), 0)
+    lo, hi = verts.reshape(-1, 3).min(0), verts.reshape(-1, 3).max(0)
+    org, d = scenes.random_rays((1 << 17) + 13, lo, hi)
+    hs = cuda.HostScene(sc)
+    out = {}
+    for lanes in ("2", "4"):
+        monkeypatch.setenv("IZPI_TRACE_LANES", lanes)
+        c = cuda.Context(0)
+        c.upload(hs)
+        ids, t, st = c.trace_closest(org, d, stats=True)
+        ids2, t2 = c.trace_closest(org, d)
+        ids3, t3 = c.trace_closest(org, d, mode=cuda.TRACE_FP32)
+        assert ids2.tobytes() == ids.tobytes() and t2.tobytes() == t.tobytes()
+        out[lanes] = (ids, t, st["nodes"], st["prims"], ids3)
+        c.close()
+    assert out["2"][0].tobytes() == out["4"][0].tobytes() and out["2"][1].tobytes() == out["4"][1].tobytes()
+    assert out["2"][2] == out["4"][2] and out["2"][3] == out["4"][3]
+    assert out["2"][4].tobytes() == out["4"][4].tobytes()  # the fp32 variants agree with each other as well
+    oi, ot, ost = oracle_mod.OracleScene(sc).trace(org, d, stats=True)
+    assert out["2"][0].tobytes() == oi.tobytes() and out["2"][1].tobytes() == ot.tobytes()
+    assert out["2"][2] == ost["nodes"] and out["2"][3] == ost["tris"] + ost["spheres"] + ost["others"]
