@@ -373,7 +373,8 @@ int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double
   // enough to keep the persistent kernel's tail small.
   cudaStream_t ss[2] = {ctx->stream, ctx->stream2};
   int k = 0;
-  int64_t slice = 1 << 18;
+  int64_t slice = 1 << 18, slice_max = 1 << 21;
+  if (const char* e = getenv("IZPI_TRACE_SLICE_LOG2")) { int v = atoi(e); if (v >= 18 && v <= 26) slice_max = (int64_t)1 << v; }
   for (int64_t b = 0; b < n; k ^= 1) {
     int64_t m = n - b < slice ? n - b : slice;
     cudaStream_t st = ss[k];
@@ -385,7 +386,7 @@ int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double
     IZ_CUDA(cudaMemcpyAsync(prim_id + b, ctx->d_ids + b, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     IZ_CUDA(cudaMemcpyAsync(t + b, ctx->d_t + b, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
     b += m;
-    if (slice < (1 << 21)) slice <<= 1;
+    if (slice < slice_max) slice <<= 1;
   }
   IZ_CUDA(cudaStreamSynchronize(ss[0]));
   IZ_CUDA(cudaStreamSynchronize(ss[1]));
