@@ -92,7 +92,9 @@ __device__ __forceinline__ void g2_node_phase(G4State& s, const DScene& sc, int2
     int ref0 = 0, ref1 = 0;
     if (in_node) {
       const float4* np = sc.nodes_t + (size_t)s.cur * 8 + 4 * j;
-      const float4 a0 = __ldg(np), b0 = __ldg(np + 1), a1 = __ldg(np + 2), b1 = __ldg(np + 3);
+      float4 a0, b0, a1, b1;
+      g4_load_child(np, a0, b0);
+      g4_load_child(np + 2, a1, b1);
       ref0 = __float_as_int(b0.z); ref1 = __float_as_int(b1.z);
       if (COUNT) n_nodes++;
       const float tmaxf = (float)s.tmax;  // float32(tMax) at node entry (bvh4.go:100)

@@ -67,6 +67,14 @@ __device__ __forceinline__ void g4_begin(G4State& s, const DScene& sc, const DRa
            fabsf(iz) <= 3.0e38f && ix != 0.0f && iy != 0.0f && iz != 0.0f;
 }
 
+// One 32-byte child record of the child-major node copy in a single 256-bit load (sm_100: LDG.E.256): half the load
+// instructions and half the L1 tag look-ups of two 128-bit loads.  p must be 32-byte aligned (it is: 128-byte nodes).
+__device__ __forceinline__ void g4_load_child(const float4* p, float4& a, float4& b) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+}
+
 // Pop until something to do is found; leaves the ray idle when the stack is empty.
 template <bool COUNT>
 __device__ __forceinline__ void g4_pop(G4State& s, const DScene& sc, const int2* stack, int j, uint32_t& n_nodes) {
@@ -99,8 +107,8 @@ __device__ __forceinline__ void g4_node_phase(G4State& s, const DScene& sc, int2
     int ref = 0;
     if (in_node) {
       const float4* np = sc.nodes_t + (size_t)s.cur * 8 + 2 * j;
-      const float4 a = __ldg(np);
-      const float4 b = __ldg(np + 1);
+      float4 a, b;
+      g4_load_child(np, a, b);
       ref = __float_as_int(b.z);  // inner child: node index; leaf child: ~((first primitive << 2) | (count - 1)), built at upload
       if (COUNT) n_nodes++;
       const float tmaxf = (float)s.tmax;  // float32(tMax) at node entry (bvh4.go:100)
