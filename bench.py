@@ -303,6 +303,11 @@ def main():
     render_info = bench_render(ctx, cuda, scenes, world, rank, barrier, with_4k=not args.no_4k)
     ctx.upload(hs)  # back to the closest-hit scene for the CPU-baseline parity check below
 
+    # FLOP side of the traversal roofline (north_star: "the slower of bytes per ray at HBM bandwidth and intersection FLOPs at
+    # fp64/fp32 peak"): measured dependent-FMA peaks of this GPU, SURVEY.md §8(d)'s operation counts per visit / per test
+    fp32_peak, fp64_peak = ctx.fma_peak(False), ctx.fma_peak(True)
+    fp32_flop_per_ray, fp64_flop_per_ray = 100.0 * nodes_per_ray, 50.0 * prims_per_ray
+
     if world > 1:
         tt = torch.tensor([total_ms, e2e_ms, kernel_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -321,6 +326,11 @@ def main():
                        "algorithmic_bytes_per_ray": bytes_per_ray},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": ncu_traffic(n)[0], "kernel": ncu_traffic(n)[1], "kernel_ms": kernel_ms, "peak_source": peak_src},
+            "roofline_flops": {"fp32_tflops_peak": fp32_peak, "fp64_tflops_peak": fp64_peak, "fp32_flop_per_ray": fp32_flop_per_ray,
+                               "fp64_flop_per_ray": fp64_flop_per_ray,
+                               "mrays_per_s_at_flop_peak": 1e-6 / (fp32_flop_per_ray / (fp32_peak * 1e12) + fp64_flop_per_ray / (fp64_peak * 1e12)),
+                               "mrays_per_s_at_hbm_peak": hbm * 1e3 / bytes_per_ray,
+                               "note": "the byte side is the slower (binding) one; peaks measured by izpi_debug_fma_peak on this GPU"},
             "e2e": {"value": world * n * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 48,
                     "d2h_bytes_per_step": n * 12},
             "gpu_launches": int(launches),

@@ -163,6 +163,10 @@ int izpi_bvh4_build_fetch(izpi_ctx* ctx, izpi_bvh4_node* nodes, int32_t* perm);
 int izpi_debug_ray_aabb4(izpi_ctx* ctx, int32_t n, const float* org, const float* inv, const float* bounds,
                          const float* tmax, uint8_t* masks);
 
+/* Diagnostic: measured dependent-FMA throughput (TFLOP/s, 2 flops per FMA) of the fp32 (fp64 = 0) or fp64 (fp64 = 1) vector
+ * pipe of the context's device: the FLOP side of the traversal roofline (BASELINE north_star). */
+int izpi_debug_fma_peak(izpi_ctx* ctx, int fp64, double* tflops);
+
 /* ---- tile rendering --------------------------------------------------------------------- */
 #define IZPI_SAMPLER_COLOUR 0   /* sampler/colour.go   */
 #define IZPI_SAMPLER_SPECTRAL 1 /* sampler/spectral.go */

@@ -259,6 +259,25 @@ __global__ void box4_kernel(int n, const float* __restrict__ org, const float* _
   masks[i] = m;
 }
 
+
+// Diagnostic: dependent-FMA throughput of the fp32 / fp64 vector pipes (the FLOP side of the traversal
+// roofline; MEASURED_PEAKS.json carries HBM and tensor-core peaks only).  16 independent chains per thread.
+template <typename T>
+__global__ void fma_peak_kernel(int iters, T seed, T* out) {
+  T a[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) a[k] = seed + (T)(threadIdx.x + k);
+  const T m = (T)1.0000001, c = (T)1e-7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = fma(a[k], m, c);
+  }
+  T acc = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) acc += a[k];
+  if (acc == (T)12345.678) out[0] = acc;  // keeps the chains alive
+}
+
 int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir, double tmin, double tmax,
                  int mode, int32_t* d_ids, double* d_t, cudaStream_t st, bool count, unsigned long long* counters) {
   if (mode != IZPI_TRACE_EXACT && mode != IZPI_TRACE_FP32) { set_error("izpi_trace_closest: unknown mode"); return IZPI_EINVAL; }
@@ -412,6 +431,31 @@ int izpi_debug_ray_aabb4(izpi_ctx* ctx, int32_t n, const float* org, const float
   IZ_CUDA(cudaStreamSynchronize(ctx->stream));
   IZ_CUDA(cudaMemcpy(masks, d_m, (size_t)n, cudaMemcpyDeviceToHost));
   cudaFree(d_o); cudaFree(d_i); cudaFree(d_b); cudaFree(d_t); cudaFree(d_m);
+  return IZPI_OK;
+}
+
+
+int izpi_debug_fma_peak(izpi_ctx* ctx, int fp64, double* tflops) {
+  if (!ctx || !tflops) { set_error("izpi_debug_fma_peak: bad argument"); return IZPI_EINVAL; }
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  void* d_out = nullptr;
+  IZ_CUDA(cudaMalloc(&d_out, 16));
+  const int iters = 1 << 14, threads = 256, blocks = ctx->sm_count * 8;
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    IZ_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (fp64) fma_peak_kernel<double><<<blocks, threads, 0, ctx->stream>>>(iters, 1.0, static_cast<double*>(d_out));
+    else fma_peak_kernel<float><<<blocks, threads, 0, ctx->stream>>>(iters, 1.0f, static_cast<float*>(d_out));
+    IZ_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    IZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    IZ_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->launches++;
+    double tf = 2.0 * 16.0 * (double)iters * threads * (double)blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaFree(d_out);
+  *tflops = best;
   return IZPI_OK;
 }
 

@@ -42,7 +42,7 @@ class RenderConfig(C.Structure):
 EXPORTS = [
     "izpi_last_error", "izpi_version", "izpi_ctx_create", "izpi_ctx_destroy", "izpi_scene_upload",
     "izpi_trace_closest", "izpi_trace_closest_device", "izpi_launch_count", "izpi_render_setup", "izpi_render_tiles", "izpi_render_tile_rows",
-    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_displace", "izpi_displace_fetch", "izpi_bvh4_build", "izpi_bvh4_build_fetch",
+    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_debug_fma_peak", "izpi_displace", "izpi_displace_fetch", "izpi_bvh4_build", "izpi_bvh4_build_fetch",
     "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
     "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
     "izpi_host_tiles", "izpi_host_render",
@@ -77,6 +77,7 @@ def lib():
     L.izpi_launch_count.argtypes = [C.c_void_p]
     L.izpi_launch_count.restype = C.c_uint64
     L.izpi_debug_ray_aabb4.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.izpi_debug_fma_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.izpi_displace.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_double,
                                 C.c_int, C.POINTER(C.c_int64)]
     L.izpi_displace_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -224,6 +225,12 @@ class Context:
         perm = np.zeros(len(b), dtype=np.int32)
         check(lib().izpi_bvh4_build_fetch(self._h, nodes.ctypes.data, perm.ctypes.data))
         return nodes, perm
+
+    def fma_peak(self, fp64: bool) -> float:
+        """Measured dependent-FMA TFLOP/s of the fp32 / fp64 vector pipe (the FLOP side of the traversal roofline)."""
+        v = C.c_double()
+        check(lib().izpi_debug_fma_peak(self._h, int(fp64), C.byref(v)))
+        return v.value
 
     def debug_ray_aabb4(self, org, inv, bounds, tmax):
         o = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)
