@@ -220,3 +220,9 @@ def test_lane_layouts_agree(oracle_mod, monkeypatch):
     oi, ot, ost = oracle_mod.OracleScene(sc).trace(org, d, stats=True)
     assert out["2"][0].tobytes() == oi.tobytes() and out["2"][1].tobytes() == ot.tobytes()
     assert out["2"][2] == ost["nodes"] and out["2"][3] == ost["tris"] + ost["spheres"] + ost["others"]
+
+
+def test_fma_peak_diagnostic(ctx):
+    """The FLOP side of the roofline is measured, not assumed: plausible B200 vector peaks (nominal 80 / 40 TFLOP/s)."""
+    f32, f64 = ctx.fma_peak(False), ctx.fma_peak(True)
+    assert 20.0 < f32 < 120.0 and 10.0 < f64 < 60.0 and f32 > f64
