@@ -284,7 +284,12 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
 
 // The same stage with two lanes per path (intersect_g2.cuh): 16 paths per warp.  Used when the tree's worst-case stack fits
 // the kG2Stack-entry slab (launch_cfg); trace.cu explains the trade.
-__global__ void __launch_bounds__(kThreads, 6)
+constexpr int kExt2Threads = 64;  // two-warp blocks, 14 per SM at 72 registers (trace.cu explains the choice)
+
+#ifndef IZPI_EXT2_MIN_BLOCKS
+#define IZPI_EXT2_MIN_BLOCKS 14
+#endif
+__global__ void __launch_bounds__(kExt2Threads, IZPI_EXT2_MIN_BLOCKS)
 extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q, int stragglers) {
   extern __shared__ int2 g4_stack_smem[];
   constexpr int kSlots = G2Slab<kG2Stack>::kSlots;
@@ -293,7 +298,7 @@ extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
   const int j = lane & 1, pshift = (int)(lane & ~1u);
   int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 1) * kSlots;
   const int n = (int)q.counters[0];  // live paths of this bounce (a batch holds < 2^31 paths)
-  const int warps = (int)gridDim.x * (kThreads / 32);
+  const int warps = (int)gridDim.x * (kExt2Threads / 32);
   int chunk = (n / (warps * 4) + 15) & ~15;
   chunk = chunk < 16 ? 16 : (chunk > kExtendChunk ? kExtendChunk : chunk);
   uint32_t nn = 0, np = 0;
@@ -744,11 +749,11 @@ struct LaunchCfg {
 int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
   lc.smem = (size_t)kStackDepth * kThreads * sizeof(int32_t);
   lc.smem4 = (size_t)(kThreads / 4) * kG4Slab * sizeof(int2);
-  lc.smem2 = (size_t)(kThreads / 2) * G2Slab<kG2Stack>::kSlots * sizeof(int2);
+  lc.smem2 = (size_t)(kExt2Threads / 2) * G2Slab<kG2Stack>::kSlots * sizeof(int2);
   static thread_local int ext_blocks = 0, ext4_blocks = 0, ext2_blocks = 0;
   if (!ext_blocks) {
     IZ_CUDA(cudaFuncSetAttribute(extend_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem2));
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext2_blocks, extend_g2_kernel, kThreads, lc.smem2));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext2_blocks, extend_g2_kernel, kExt2Threads, lc.smem2));
     if (ext2_blocks < 1) ext2_blocks = 1;
     IZ_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_blocks, extend_kernel, kThreads, lc.smem));
@@ -797,9 +802,9 @@ int batch_step(izpi_ctx* ctx, RenderState* r, BatchSlot& s, const LaunchCfg& lc)
   int rc;
   long long want = ((long long)s.live + kThreads - 1) / kThreads;
   if (lc.use_g2) {
-    long long want2 = ((long long)s.live + (kThreads / 2) - 1) / (kThreads / 2);
+    long long want2 = ((long long)s.live + (kExt2Threads / 2) - 1) / (kExt2Threads / 2);
     int eg2 = (int)std::max<long long>(1, std::min<long long>(want2, (long long)sm * lc.ext2_blocks));
-    if ((rc = launch(ctx, st, extend_g2_kernel, dim3(eg2), dim3(kThreads), lc.smem2, ctx->scene, r->rp, s.d_paths, s.q,
+    if ((rc = launch(ctx, st, extend_g2_kernel, dim3(eg2), dim3(kExt2Threads), lc.smem2, ctx->scene, r->rp, s.d_paths, s.q,
                      ctx->pair_stragglers)) != IZPI_OK) return rc;
   } else if (lc.use_g4) {
     long long want4 = ((long long)s.live + (kThreads / 4) - 1) / (kThreads / 4);

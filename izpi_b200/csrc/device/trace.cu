@@ -142,12 +142,19 @@ trace_g4_kernel(const __grid_constant__ DScene sc, long long n, const double* __
 
 // ---- 2 lanes per ray --------------------------------------------------------------------------
 // Sixteen ray slots per warp (intersect_g2.cuh); same queue, same replacement scheme as the 4-lane kernel.
-#ifndef IZPI_G2_MIN_BLOCKS
-#define IZPI_G2_MIN_BLOCKS 6
+// Blocks of two warps: 14 of them fit an SM at 72 registers without spills (28 warps; 13-14 blocks: 740 Mrays/s), where
+// blocks of four warps stop at 6 x 4 = 24 warps with 78 registers (681) or spill at 7 x 4 (668); 16 x 2 warps at 64
+// registers spill and fall to 616.
+#ifndef IZPI_G2_THREADS
+#define IZPI_G2_THREADS 64
 #endif
+#ifndef IZPI_G2_MIN_BLOCKS
+#define IZPI_G2_MIN_BLOCKS 14
+#endif
+constexpr int kG2Threads = IZPI_G2_THREADS;
 
 template <bool COUNT, bool F32, int STACK>
-__global__ void __launch_bounds__(kTraceThreads, IZPI_G2_MIN_BLOCKS)
+__global__ void __launch_bounds__(kG2Threads, IZPI_G2_MIN_BLOCKS)
 trace_g2_kernel(const __grid_constant__ DScene sc, long long n, const double* __restrict__ org,
                 const double* __restrict__ dir, double tmin, double tmax, int32_t* __restrict__ ids,
                 double* __restrict__ ts, unsigned long long* counters, int stragglers) {
@@ -157,7 +164,7 @@ trace_g2_kernel(const __grid_constant__ DScene sc, long long n, const double* __
   const int j = lane & 1, pshift = (int)(lane & ~1u);
   int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 1) * kSlots;
   const int n32 = (int)n;
-  const int warps = (int)gridDim.x * (kTraceThreads / 32);
+  const int warps = (int)gridDim.x * (kG2Threads / 32);
   int chunk = (n32 / (warps * 4) + 15) & ~15;  // rays per atomicAdd: shrinks for small batches (tail balance)
   chunk = chunk < 16 ? 16 : (chunk > kChunk ? kChunk : chunk);
   uint32_t n_nodes = 0, n_prims = 0;
@@ -225,23 +232,23 @@ trace_g2_kernel(const __grid_constant__ DScene sc, long long n, const double* __
 template <int STACK>
 int launch_g2(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir, double tmin, double tmax, int mode, int32_t* d_ids,
               double* d_t, cudaStream_t st, bool count, unsigned long long* counters) {
-  const size_t smem = (size_t)(kTraceThreads / 2) * G2Slab<STACK>::kSlots * sizeof(int2);
+  const size_t smem = (size_t)(kG2Threads / 2) * G2Slab<STACK>::kSlots * sizeof(int2);
   auto k = mode == IZPI_TRACE_FP32 ? trace_g2_kernel<false, true, STACK> : (count ? trace_g2_kernel<true, false, STACK> : trace_g2_kernel<false, false, STACK>);
   static thread_local int bps = 0;
   if (!bps) {
     IZ_CUDA(cudaFuncSetAttribute(trace_g2_kernel<false, false, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IZ_CUDA(cudaFuncSetAttribute(trace_g2_kernel<true, false, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IZ_CUDA(cudaFuncSetAttribute(trace_g2_kernel<false, true, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, trace_g2_kernel<false, false, STACK>, kTraceThreads, smem));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, trace_g2_kernel<false, false, STACK>, kG2Threads, smem));
     if (bps < 1) bps = 1;
   }
   int use_bps = bps;
   if (const char* e = getenv("IZPI_TRACE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < use_bps) use_bps = v; }
-  long long want = (n + (kTraceThreads / 2) - 1) / (kTraceThreads / 2);
+  long long want = (n + (kG2Threads / 2) - 1) / (kG2Threads / 2);
   long long grid = (long long)ctx->sm_count * use_bps;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  k<<<(unsigned)grid, kTraceThreads, smem, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, counters, ctx->pair_stragglers);
+  k<<<(unsigned)grid, kG2Threads, smem, st>>>(ctx->scene, (long long)n, d_org, d_dir, tmin, tmax, d_ids, d_t, counters, ctx->pair_stragglers);
   IZ_CUDA(cudaGetLastError());
   ctx->launches++;
   return IZPI_OK;
