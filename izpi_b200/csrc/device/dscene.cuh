@@ -63,7 +63,7 @@ struct izpi_ctx {
   cudaStream_t stream2 = nullptr;  // second lane of the copy/compute pipeline of izpi_trace_closest
   bool has_scene = false;
   int node_stragglers = 4;    // IZPI_NODE_STRAGGLERS: node-phase exit threshold of the 4-lanes-per-ray kernels
-  int pair_stragglers = 6;    // IZPI_PAIR_STRAGGLERS: the same for the 2-lanes-per-ray kernel (pairs)
+  int pair_stragglers = 7;    // IZPI_PAIR_STRAGGLERS: the same for the 2-lanes-per-ray kernel (pairs)
   int trace_lanes = 2;        // IZPI_TRACE_LANES=2|4: lanes per ray of izpi_trace_closest
   bool force_scalar = false;  // IZPI_FORCE_SCALAR=1: thread-per-ray traversal even for reference-shaped trees
   izpi::DScene scene{};

@@ -20,7 +20,7 @@ namespace izpi {
 #define IZPI_G2_STACK 48  // measured on config 2: 40 -> 680, 48 -> 678, 56 -> 668 Mrays/s; 64 would leave room for 5 blocks only
 #endif
 constexpr int kG2Stack = IZPI_G2_STACK;      // stack entries of the 2-lane kernel's slab; deeper trees use the 4-lane kernel (64 entries)
-constexpr int kG2Stragglers = 6;  // leave the node phase when <= this many PAIRS are still in it while leaves are pending
+constexpr int kG2Stragglers = 7;  // leave the node phase when <= this many PAIRS are still in it while leaves are pending
 
 template <int STACK>
 struct G2Slab {
