@@ -184,11 +184,31 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port",
                              "sample": f"{n_sample} of the step's {N_RAYS} rays per step, all host threads"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on some boxes), so
+    file descriptor 1 is pointed at stderr for the whole run and the result line goes to a private copy of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -346,7 +366,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port",
                                     "sample": f"first {n_cpu} rays of the step, {threads} host threads; C++ restatement of the Go CPU path",
                                     "parity_on_sample": bool(np.array_equal(gi, oi) and gt.tobytes() == ot.tobytes())}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
