@@ -50,9 +50,10 @@ typedef struct izpi_proto_image {
 
 /* An entry of the light-source library (internal/lightsources/lightsources.go:6-466) for
  * SpectralConstantTexture.from_light_source_library.  Built in: the three blackbodies (incandescent_2800k, halogen_3200k,
- * cie_illuminant_a_2856k: spectral.NewBlackbodySPD, spectral.go:275-320) and cie_f1_daylight_fluorescent; any other name
- * must be supplied here, otherwise the conversion FAILS (the reference would silently substitute illuminant A for names it
- * does not know, transport.go:483-490 -- a silent substitution for names it DOES know would change the image). */
+ * cie_illuminant_a_2856k: spectral.NewBlackbodySPD, spectral.go:275-320) and cie_f1_daylight_fluorescent.  The other 38 keys
+ * of the reference's library must be supplied here, otherwise the conversion FAILS (their measured tables are not carried by
+ * this library, and substituting something else would change the image).  A name that is in neither place is unknown to the
+ * reference too, which falls back to CIE illuminant A (transport.go:483-490); so does this library. */
 typedef struct izpi_proto_spd {
   const char* name;
   int32_t n;

@@ -634,7 +634,23 @@ struct Builder {
       else if (name == "halogen_3200k") blackbody(3200, w, v);
       else if (name == "cie_illuminant_a_2856k") blackbody(2856, w, v);
       else if (name == "cie_f1_daylight_fluorescent") { w.resize(75); for (int i = 0; i < 75; i++) w[i] = 380.0 + 5.0 * i; v.assign(kCieF1, kCieF1 + 75); }
-      else return fail("light source \"" + name + "\" is not built in; supply its SPD in izpi_proto_options.light_sources");
+      else {
+        // Keys of the reference's library (lightsources.go:6-466) whose measured tables are not carried here: converting them
+        // needs the SPD from the caller.  Any OTHER name is unknown to the reference as well, which then falls back to CIE
+        // illuminant A with a warning (transport.go:483-490; TestLightSourceLibraryIntegration expects success) -- same here.
+        static const char* const kReferenceKeys[] = {
+            "hy_cree_llf_tm_30_90", "hy_ngl_47_tm_30_92", "pc_ngl_124_tm_30_194", "pc_ngl_308_tm_30_231", "pcv_soraa_prem_2700_k_tm_30_294",
+            "pcv_soraa_vivid_2700_k_tm_30_296", "hy_ge_lumination", "pc_maxled", "hy_cree_module", "pc_current_ge", "cm_lumenetix",
+            "cm_acuity_evo_4", "cm_intense_mxrtr2", "pc_samjin", "cm_edison_price_lumenetix", "cm_pathway_lexel", "pc_green_creative_mr16",
+            "pc_soraa_mr16_830", "hy_cree_par38", "pc_seoul_sunlike_3030", "cie_f2_cool_white_fluorescent", "cie_f3_white_fluorescent",
+            "cie_f4_warm_white_fluorescent", "cie_f5_daylight_fluorescent", "cie_f6_lite_white_fluorescent", "cie_f7_broadband_daylight",
+            "cie_f8_broadband_cool_white", "cie_f9_broadband_cool_white_deluxe", "cie_f10_narrowband_5000k", "cie_f11_narrowband_4000k",
+            "cie_f12_narrowband_3000k", "hps_cie238", "hps_c100s54_standard", "hps_sdw_t_100w", "incandescent_halogen_real",
+            "incandescent_krypton_real", "incandescent_60w_a19_real", "laser_red_650nm"};
+        for (const char* k : kReferenceKeys)
+          if (name == k) return fail("light source \"" + name + "\" is not built in; supply its SPD in izpi_proto_options.light_sources");
+        blackbody(2856, w, v);
+      }
       out = tabulated(std::move(w), std::move(v));
       return true;
     }

@@ -80,6 +80,10 @@ def lib():
         L.oracle_apply_displacement.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_double,
                                                 C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.oracle_free.argtypes = [C.c_void_p]
+        L.oracle_displacement_tessellate.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_displacement_apply_tessellation.restype = C.c_int64
+        L.oracle_displacement_apply_tessellation.argtypes = [C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.oracle_displacement_apply_displacement.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
         L.oracle_tiles.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
@@ -111,6 +115,30 @@ def apply_displacement(tris15, materials, pixels, dmin, dmax, per_triangle=True)
     lib().oracle_free(ot)
     lib().oracle_free(om)
     return out, outm
+
+
+def displacement_tessellate(tri15):
+    """tessellate() (displacement.go:36-103)."""
+    t = np.ascontiguousarray(tri15, dtype=np.float64).reshape(15)
+    out = np.zeros((4, 15))
+    lib().oracle_displacement_tessellate(t.ctypes.data, out.ctypes.data)
+    return out
+
+
+def displacement_apply_tessellation(tris15, max_delta_u, max_delta_v, rgb, dmin, dmax, threshold) -> int:
+    """applyTessellation() over a constant texture with explicit UV limits (displacement.go:188-218)."""
+    t = np.ascontiguousarray(tris15, dtype=np.float64).reshape(-1, 15)
+    c = np.ascontiguousarray(rgb, dtype=np.float64)
+    return int(lib().oracle_displacement_apply_tessellation(len(t), t.ctypes.data, max_delta_u, max_delta_v, c.ctypes.data, dmin, dmax, threshold))
+
+
+def displacement_apply_displacement(tris15, rgb, dmin, dmax):
+    """applyDisplacement() over a constant texture (displacement.go:201-280)."""
+    t = np.ascontiguousarray(tris15, dtype=np.float64).reshape(-1, 15)
+    c = np.ascontiguousarray(rgb, dtype=np.float64)
+    out = np.zeros_like(t)
+    lib().oracle_displacement_apply_displacement(len(t), t.ctypes.data, c.ctypes.data, dmin, dmax, out.ctypes.data)
+    return out
 
 
 class OracleScene:

@@ -488,12 +488,12 @@ void displaceOne(const MinimalTriangle& t, const Texture& map, double mn, double
   double o[15] = {p0.X, p0.Y, p0.Z, p1.X, p1.Y, p1.Z, p2.X, p2.Y, p2.Z, t.u0, t.v0, t.u1, t.v1, t.u2, t.v2};
   std::memcpy(out15, o, sizeof(o));
 }
-void applyOne(std::vector<MinimalTriangle> in, const Texture& map, double mn, double mx, std::vector<double>& out, std::vector<int32_t>& mats) {
-  double maxDeltaU = 4.0 / (double)(map.sizeX - 1), maxDeltaV = 4.0 / (double)(map.sizeY - 1);  // displacement.go:176-178
-  const double adaptiveThreshold = 2.0;
+// applyTessellation (displacement.go:188-218)
+std::vector<MinimalTriangle> applyTessellation(std::vector<MinimalTriangle> in, double maxDeltaU, double maxDeltaV, const Texture& map, double mn,
+                                               double mx, double adaptiveThreshold) {
   std::vector<MinimalTriangle> done;
   int level = 0;
-  while (!in.empty()) {  // applyTessellation (displacement.go:188-218)
+  while (!in.empty()) {
     // (the reference loops forever when two ADJACENT texels differ by more than threshold/|max-min|: a triangle
     // straddling them never passes; such maps are invalid inputs and are cut off here)
     if (++level > 40 || in.size() > (1u << 25)) { in.clear(); break; }
@@ -505,12 +505,25 @@ void applyOne(std::vector<MinimalTriangle> in, const Texture& map, double mn, do
     }
     in.swap(toIn);
   }
-  for (const MinimalTriangle& t : done) {
+  return done;
+}
+void applyOne(std::vector<MinimalTriangle> in, const Texture& map, double mn, double mx, std::vector<double>& out, std::vector<int32_t>& mats) {
+  double maxDeltaU = 4.0 / (double)(map.sizeX - 1), maxDeltaV = 4.0 / (double)(map.sizeY - 1);  // displacement.go:176-178
+  const double adaptiveThreshold = 2.0;
+  for (const MinimalTriangle& t : applyTessellation(std::move(in), maxDeltaU, maxDeltaV, map, mn, mx, adaptiveThreshold)) {
     double o[15];
     displaceOne(t, map, mn, mx, o);
     out.insert(out.end(), o, o + 15);
     mats.push_back(t.material);
   }
+}
+MinimalTriangle mt_from15(const double* p, int32_t material) {
+  return MinimalTriangle{V(p[0], p[1], p[2]), V(p[3], p[4], p[5]), V(p[6], p[7], p[8]), material, p[9], p[11], p[13], p[10], p[12], p[14]};
+}
+void mt_to15(const MinimalTriangle& t, double* o) {
+  const double v[15] = {t.vertex0.X, t.vertex0.Y, t.vertex0.Z, t.vertex1.X, t.vertex1.Y, t.vertex1.Z, t.vertex2.X, t.vertex2.Y, t.vertex2.Z,
+                        t.u0, t.v0, t.u1, t.v1, t.u2, t.v2};
+  std::memcpy(o, v, sizeof(v));
 }
 }  // namespace
 
@@ -535,4 +548,25 @@ int64_t oracle_apply_displacement(int64_t n, const double* tris, const int32_t* 
   return (int64_t)om.size();
 }
 void oracle_free(void* p) { std::free(p); }
+
+// ---- the internal steps, exposed so that the reference's own unit vectors (displacement_test.go) can be replayed -----------
+// tessellate() (displacement.go:36-103): one triangle (15 doubles) -> four
+void oracle_displacement_tessellate(const double* in15, double* out60) {
+  MinimalTriangle ch[4];
+  tessellate(mt_from15(in15, 0), ch);
+  for (int k = 0; k < 4; k++) mt_to15(ch[k], out60 + 15 * k);
+}
+// applyTessellation() with explicit limits over a CONSTANT texture (displacement_test.go:84-157); returns the triangle count
+int64_t oracle_displacement_apply_tessellation(int64_t n, const double* tris15, double maxDeltaU, double maxDeltaV, const double* rgb,
+                                               double mn, double mx, double adaptiveThreshold) {
+  Texture map; map.type = IZPI_TEX_CONSTANT; map.color = V(rgb[0], rgb[1], rgb[2]);
+  std::vector<MinimalTriangle> in;
+  for (int64_t i = 0; i < n; i++) in.push_back(mt_from15(tris15 + 15 * i, 0));
+  return (int64_t)applyTessellation(std::move(in), maxDeltaU, maxDeltaV, map, mn, mx, adaptiveThreshold).size();
+}
+// applyDisplacement() over a CONSTANT texture, no tessellation (displacement_test.go:159-213): n triangles in, n out
+void oracle_displacement_apply_displacement(int64_t n, const double* tris15, const double* rgb, double mn, double mx, double* out15) {
+  Texture map; map.type = IZPI_TEX_CONSTANT; map.color = V(rgb[0], rgb[1], rgb[2]);
+  for (int64_t i = 0; i < n; i++) displaceOne(mt_from15(tris15 + 15 * i, 0), map, mn, mx, out15 + 15 * i);
+}
 }

@@ -82,3 +82,54 @@ def test_device_displacement_edge_cases(ctx, oracle_mod):
     assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
     with pytest.raises(cuda.IzpiError):
         ctx.apply_displacement(_quad(), [0, 0], np.ones((1, 1, 4)), 0, 1)  # resU-1 == 0 in displacement.go:177
+
+
+# ---- the reference's own unit vectors (internal/displacement/displacement_test.go), replayed on the oracle ----------------
+def _tri15(v0, v1, v2, u0=0.0, v0_=0.0, u1=0.0, v1_=0.0, u2=0.0, v2_=0.0):
+    return np.array([*v0, *v1, *v2, u0, v0_, u1, v1_, u2, v2_], dtype=np.float64)
+
+
+_XY_TRIANGLE = _tri15((-1, 0, 0), (1, 0, 0), (0, 1, 0), u1=1.0, u2=0.5, v2_=1.0)  # displacement_test.go:21-28
+
+
+def test_reference_vectors_tessellate(oracle_mod):
+    """TestTessellate (displacement_test.go:13-82): the four children of the XY-plane triangle, exact."""
+    got = oracle_mod.displacement_tessellate(_XY_TRIANGLE)
+    want = np.array([
+        _tri15((-1, 0, 0), (0, 0, 0), (-0.5, 0.5, 0), u1=0.5, u2=0.25, v2_=0.5),
+        _tri15((0, 0, 0), (0.5, 0.5, 0), (-0.5, 0.5, 0), u0=0.5, u1=0.75, u2=0.25, v1_=0.5, v2_=0.5),
+        _tri15((0, 0, 0), (1, 0, 0), (0.5, 0.5, 0), u0=0.5, u1=1.0, u2=0.75, v2_=0.5),
+        _tri15((-0.5, 0.5, 0), (0.5, 0.5, 0), (0, 1, 0), u0=0.25, u1=0.75, u2=0.5, v0_=0.5, v1_=0.5, v2_=1.0),
+    ])
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("res_u,res_v,want", [(3, 3, 4), (4, 2, 16), (2, 4, 16)])
+def test_reference_vectors_apply_tessellation(oracle_mod, res_u, res_v, want):
+    """TestApplyTessellation (displacement_test.go:84-157): flat map (0, 0, 0.5), min 0, max 1, threshold 0.01,
+    maxDelta = 1 / (res - 1)."""
+    n = oracle_mod.displacement_apply_tessellation(_XY_TRIANGLE, 1.0 / (res_u - 1), 1.0 / (res_v - 1), (0.0, 0.0, 0.5), 0.0, 1.0, 0.01)
+    assert n == want
+
+
+@pytest.mark.parametrize("rgb,dmin,dmax,y", [((0.0, 0.0, 1.0), 0.0, 1.0, -1.0), ((1.0, 1.0, 1.0), -0.5, 0.5, -0.5)])
+def test_reference_vectors_apply_displacement(oracle_mod, rgb, dmin, dmax, y):
+    """TestApplyDisplacement (displacement_test.go:159-213): the XZ-plane triangle moves along its normal (-Y) by
+    min + (max - min) * blue."""
+    tri = _tri15((-1, 0, 0), (1, 0, 0), (0, 0, 1), u1=1.0, u2=0.5, v2_=1.0)
+    got = oracle_mod.displacement_apply_displacement(tri, rgb, dmin, dmax)
+    want = _tri15((-1, y, 0), (1, y, 0), (0, y, 1), u1=1.0, u2=0.5, v2_=1.0)
+    assert got.reshape(15).tobytes() == want.tobytes()
+
+
+@pytest.mark.gpu
+def test_device_reproduces_the_reference_vectors(ctx, oracle_mod):
+    """The same vectors through izpi_displace: a 3x3 flat map gives maxDelta = 4 / 2, so one tessellation level (4 children of
+    TestTessellate, displaced by the constant height) -- vertices must equal tessellate() + applyDisplacement() of the oracle."""
+    px = np.zeros((3, 3, 4)); px[..., 2] = 0.5; px[..., 3] = 1.0
+    out, _ = ctx.apply_displacement(_XY_TRIANGLE[None], [0], px, 0.0, 1.0)
+    kids = oracle_mod.displacement_tessellate(_XY_TRIANGLE)
+    want = oracle_mod.displacement_apply_displacement(kids, (0.0, 0.0, 0.5), 0.0, 1.0)
+    assert out.shape == (4, 15) and out.tobytes() == want.tobytes()
+    # XY-plane triangle, normal +Z: every vertex rises by 0.5
+    np.testing.assert_array_equal(out[:, [2, 5, 8]], 0.5)

@@ -482,3 +482,85 @@ def test_displace_operator_goes_through_the_device_tessellator(oracle_mod):
         proto.ProtoScene(m.SerializeToString()).to_scene(displacement_maps={"h.exr": px})
     assert "displace_ctx" in str(e.value)
     ctx.close()
+
+
+# ---- the reference's own transport tests (internal/transport/transport_test.go), replayed ---------------------------------
+def _pbr_constant_scene(spectral):
+    """TestPBRMaterialTransformation's material (transport_test.go:12-75) on one triangle."""
+    m = ps.Scene()
+    m.colour_representation = 2 if spectral else 1
+    a = m.materials["test_pbr"]
+    a.name, a.type = "test_pbr", 6
+    _vec3(a.pbr.albedo.constant.value, (1.0, 0.5, 0.2)); _vec3(a.pbr.roughness.constant.value, (0.5, 0.5, 0.5))
+    _vec3(a.pbr.metalness.constant.value, (0.0, 0.0, 0.0)); _vec3(a.pbr.normal_map.constant.value, (0.5, 0.5, 1.0))
+    _vec3(a.pbr.sss.constant.value, (0.0, 0.0, 0.0)); a.pbr.sss_radius = 0.0
+    t = m.objects.triangles.add(); t.material_name = "test_pbr"
+    _vec3(t.vertex1, (1, 0, 0)); _vec3(t.vertex2, (0, 1, 0))
+    return m
+
+
+def test_reference_pbr_material_transformation(oracle_mod):
+    """transport_test.go:12-117: RGB -> plain PBR; SPECTRAL -> PBR with a spectral albedo whose value lies in [0, 1] at 380, 550
+    and 650 nm (here: NewSpectralNeutral(luminance), transport.go:514-519)."""
+    _, mats, texs, stex = spec_view(proto.ProtoScene(_pbr_constant_scene(False).SerializeToString()).to_scene().to_c())
+    assert mats[0].type == S.MAT_PBR and mats[0].spectral_tex == -1
+    assert texture_desc(texs, mats[0].tex) == ("const", (f32(1.0), f32(0.5), f32(0.2)))
+    assert texture_desc(texs, mats[0].normal_tex) == ("const", (0.5, 0.5, 1.0))
+    sc = proto.ProtoScene(_pbr_constant_scene(True).SerializeToString()).to_scene()
+    _, mats, texs, stex = spec_view(sc.to_c())
+    assert mats[0].type == S.MAT_PBR and mats[0].spectral_tex >= 0
+    lum = 0.299 * f32(1.0) + 0.587 * f32(0.5) + 0.114 * f32(0.2)  # TestTextureToSpectralTexture's conversion (:119-138)
+    osn = oracle_mod.OracleScene(sc)
+    for lam in (380.0, 550.0, 650.0):
+        v = osn.spectral_texture_value(mats[0].spectral_tex, lam)
+        assert 0.0 <= v <= 1.0 and v == lum
+
+
+@pytest.mark.parametrize("name,known", [("incandescent_2800k", True), ("cie_illuminant_a_2856k", True), ("cie_f1_daylight_fluorescent", True),
+                                        ("nonexistent_light_source", True), ("hy_cree_llf_tm_30_90", False), ("cie_f4_warm_white_fluorescent", False)])
+def test_reference_light_source_library_integration(oracle_mod, name, known):
+    """transport_test.go:140-191: every library name -- and an unknown one, which falls back to CIE illuminant A -- gives a
+    spectral texture with values in [0, 1] at 400..700 nm.  Names of the reference's library whose tables this library does not
+    carry must be supplied by the caller; without them the conversion fails instead of substituting."""
+    m = ps.Scene()
+    a = m.materials["l"]; a.name, a.type = "l", 2
+    a.diffuselight.spectral_emit.from_light_source_library.light_source_name = name
+    s = proto.ProtoScene(m.SerializeToString())
+    if not known:
+        with pytest.raises(cuda.IzpiError):
+            s.to_scene()
+        s = proto.ProtoScene(m.SerializeToString())
+        s.to_scene(light_sources={name: (380.0 + 5.0 * np.arange(75), np.linspace(0.2, 1.0, 75))})
+    else:
+        s.to_scene()
+    _, mats, _, stex = spec_view(s.to_c())
+    osn = oracle_mod.OracleScene(s)
+    vals = [osn.spectral_texture_value(mats[0].spectral_tex, lam) for lam in (400.0, 500.0, 600.0, 700.0)]
+    assert all(0.0 <= v <= 1.0 for v in vals)
+    if name == "nonexistent_light_source":  # == illuminant A
+        m2 = ps.Scene()
+        b = m2.materials["l"]; b.name, b.type = "l", 2
+        b.diffuselight.spectral_emit.from_light_source_library.light_source_name = "cie_illuminant_a_2856k"
+        s2 = proto.ProtoScene(m2.SerializeToString()).to_scene()
+        assert spectral_desc(spec_view(s2.to_c())[3], 0) == spectral_desc(stex, 0)
+
+
+def test_reference_spectral_texture_methods(oracle_mod):
+    """transport_test.go:193-274: gaussian(1, 550, 40), neutral(0.73), tabulated {380,500,600,750} -> {0.1,0.5,0.8,0.3} evaluated
+    at 550 nm are non-negative; the closed forms pin the values."""
+    m = ps.Scene()
+    a = m.materials["g"]; a.name, a.type = "g", 4
+    a.lambert.spectral_albedo.gaussian.peak_value, a.lambert.spectral_albedo.gaussian.center_wavelength, a.lambert.spectral_albedo.gaussian.width = 1.0, 550, 40
+    b = m.materials["n"]; b.name, b.type = "n", 4; b.lambert.spectral_albedo.neutral.reflectance = 0.73
+    c = m.materials["t"]; c.name, c.type = "t", 4
+    c.lambert.spectral_albedo.tabulated.wavelengths.extend([380, 500, 600, 750]); c.lambert.spectral_albedo.tabulated.values.extend([0.1, 0.5, 0.8, 0.3])
+    s = proto.ProtoScene(m.SerializeToString()).to_scene()
+    _, mats, _, _ = spec_view(s.to_c())
+    by_name = {}
+    osn = oracle_mod.OracleScene(s)
+    for mat in mats:
+        by_name[mat.spectral_tex] = osn.spectral_texture_value(mat.spectral_tex, 550.0)
+    vals = sorted(by_name.values())
+    # gaussian at its centre = peak (1.0); neutral = float32(0.73); tabulated = lerp(500 -> 0.5, 600 -> 0.8) at 550 in float32 inputs
+    assert vals[2] == 1.0 and vals[1] == f32(0.73)
+    assert abs(vals[0] - (f32(0.5) + 0.5 * (f32(0.8) - f32(0.5)))) < 1e-15
