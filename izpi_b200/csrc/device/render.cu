@@ -299,8 +299,7 @@ extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
   int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 1) * kSlots;
   const int n = (int)q.counters[0];  // live paths of this bounce (a batch holds < 2^31 paths)
   const int warps = (int)gridDim.x * (kExt2Threads / 32);
-  int chunk = (n / (warps * 4) + 15) & ~15;
-  chunk = chunk < 16 ? 16 : (chunk > kExtendChunk ? kExtendChunk : chunk);
+  // guided self-scheduling of queue chunks (trace.cu, trace_g2_kernel): short tails for the small late-bounce launches
   uint32_t nn = 0, np = 0;
   unsigned traced = 0;
   int chunk_next = 0, chunk_end = 0;
@@ -313,8 +312,15 @@ extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
     if (idle) {
       if (chunk_next >= chunk_end && !exhausted) {
         unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(&q.counters[7], (unsigned long long)chunk);
+        int chunk = 16;
+        if (lane == 0) {
+          const long long left = (long long)n - (long long)*reinterpret_cast<volatile unsigned long long*>(&q.counters[7]);
+          long long want = left > 0 ? left / (2 * (long long)warps) : 0;
+          chunk = want > kExtendChunk ? kExtendChunk : (want < 16 ? 16 : (int)((want + 15) & ~15ll));
+          b = atomicAdd(&q.counters[7], (unsigned long long)chunk);
+        }
         b = __shfl_sync(full, b, 0);
+        chunk = __shfl_sync(full, chunk, 0);
         if (b >= (unsigned long long)n) { exhausted = true; chunk_next = chunk_end = 0; }
         else { chunk_next = (int)b; chunk_end = (int)b + chunk < n ? (int)b + chunk : n; }
       }

@@ -165,8 +165,10 @@ trace_g2_kernel(const __grid_constant__ DScene sc, long long n, const double* __
   int2* stack = g4_stack_smem + (size_t)(threadIdx.x >> 1) * kSlots;
   const int n32 = (int)n;
   const int warps = (int)gridDim.x * (kG2Threads / 32);
-  int chunk = (n32 / (warps * 4) + 15) & ~15;  // rays per atomicAdd: shrinks for small batches (tail balance)
-  chunk = chunk < 16 ? 16 : (chunk > kChunk ? kChunk : chunk);
+  // Guided self-scheduling: a warp asks for (rays still in the queue) / (2 x warps), at most kChunk and at least one
+  // full warp of pairs, so chunks shrink as the queue drains and the kernel's tail -- the time the last warps need for what
+  // they still hold -- stays short whatever the batch size (it matters for the sliced host-buffer path and for the
+  // renderer's many small launches).  The queue head is read without ordering: a stale value only changes a chunk's size.
   uint32_t n_nodes = 0, n_prims = 0;
   // cold state in shared memory (see trace_g4_kernel): ray index in the pad slot of the pair's slab, the warp's chunk cursor
   // in the pad slots of its first two slabs
@@ -188,8 +190,15 @@ trace_g2_kernel(const __grid_constant__ DScene sc, long long n, const double* __
       __syncwarp();
       if (chunk_next >= chunk_end && !exhausted) {
         unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(&counters[0], (unsigned long long)chunk);
+        int chunk = 16;
+        if (lane == 0) {
+          const long long left = (long long)n32 - (long long)*reinterpret_cast<volatile unsigned long long*>(&counters[0]);
+          long long want = left > 0 ? left / (2 * (long long)warps) : 0;
+          chunk = want > kChunk ? kChunk : (want < 16 ? 16 : (int)((want + 15) & ~15ll));
+          b = atomicAdd(&counters[0], (unsigned long long)chunk);
+        }
         b = __shfl_sync(0xffffffffu, b, 0);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (b >= (unsigned long long)n32) { exhausted = true; chunk_next = chunk_end = 0; }
         else { chunk_next = (int)b; chunk_end = (int)b + chunk < n32 ? (int)b + chunk : n32; }
       }
