@@ -166,7 +166,13 @@ int izpi_scene_upload(izpi_ctx* ctx, const izpi_scene_desc* d) {
         }
         need[i] = k > 0 ? (k - 1) + deepest : 0;
       }
-      s.g4_need = ordered && need[0] < 64 ? need[0] : 64;
+      if (ordered && need[0] > 64) {
+        // (*BVH4).Hit indexes its [64]int32 stack without a bound check and panics on such a tree (bvh4.go:71,141-145);
+        // the kernels' slabs hold 64 entries as well, so refuse it instead of corrupting shared memory
+        set_error("izpi_scene_upload: the BVH4 can need " + std::to_string(need[0]) + " traversal stack entries; the reference's stack holds 64 (bvh4.go:71)");
+        return IZPI_EINVAL;
+      }
+      s.g4_need = ordered ? need[0] : 64;
     }
     if (ok) {
       // final form of a child record: {minx miny minz maxx | maxy maxz ref cnt} with ref = node index for an inner child and
