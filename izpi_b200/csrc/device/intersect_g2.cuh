@@ -16,10 +16,14 @@
 
 namespace izpi {
 
+// Two slab sizes are compiled: 48 entries (14 two-warp blocks per SM; every NewBVH4 tree up to ~10^9 primitives, 3 entries
+// per level) and 52 entries (13 blocks, about 4 % slower on config 2) for somewhat deeper trees such as the device-built LBVH
+// of the 11.5 M-triangle mesh (51 entries); beyond that the 4-lane kernel with the reference's full 64 entries takes over.
 #ifndef IZPI_G2_STACK
-#define IZPI_G2_STACK 48  // measured on config 2: 40 -> 680, 48 -> 678, 56 -> 668 Mrays/s; 64 would leave room for 5 blocks only
+#define IZPI_G2_STACK 48
 #endif
-constexpr int kG2Stack = IZPI_G2_STACK;      // stack entries of the 2-lane kernel's slab; deeper trees use the 4-lane kernel (64 entries)
+constexpr int kG2Stack = IZPI_G2_STACK;
+constexpr int kG2StackDeep = 52;      // stack entries of the 2-lane kernel's slab; deeper trees use the 4-lane kernel (64 entries)
 constexpr int kG2Stragglers = 7;  // leave the node phase when <= this many PAIRS are still in it while leaves are pending
 
 template <int STACK>

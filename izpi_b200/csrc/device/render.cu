@@ -289,10 +289,11 @@ constexpr int kExt2Threads = 64;  // two-warp blocks, 14 per SM at 72 registers 
 #ifndef IZPI_EXT2_MIN_BLOCKS
 #define IZPI_EXT2_MIN_BLOCKS 14
 #endif
+template <int STACK>
 __global__ void __launch_bounds__(kExt2Threads, IZPI_EXT2_MIN_BLOCKS)
 extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q, int stragglers) {
   extern __shared__ int2 g4_stack_smem[];
-  constexpr int kSlots = G2Slab<kG2Stack>::kSlots;
+  constexpr int kSlots = G2Slab<STACK>::kSlots;
   const unsigned full = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const int j = lane & 1, pshift = (int)(lane & ~1u);
@@ -336,15 +337,15 @@ extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
           pi = -1;
         } else {
           if (j == 0) traced++;  // atomic.AddUint64(numRays, 1) (colour.go:38)
-          g2_begin<kG2Stack>(s, sc, path_ray(p), DBL_MAX, stack, j);
+          g2_begin<STACK>(s, sc, path_ray(p), DBL_MAX, stack, j);
         }
       }
       int take = chunk_end - chunk_next;
       chunk_next += take < total ? take : total;
       if (exhausted && __ballot_sync(full, s.cur == kIdle && pi < 0) == full) break;
     }
-    g2_node_phase<false, kG2Stack>(s, sc, stack, pshift, j, nn, stragglers);
-    g2_leaf_phase<false, false, kG2Stack>(s, sc, stack, pshift, j, nn, np, 0.001);
+    g2_node_phase<false, STACK>(s, sc, stack, pshift, j, nn, stragglers);
+    g2_leaf_phase<false, false, STACK>(s, sc, stack, pshift, j, nn, np, 0.001);
     const bool done = s.cur == kIdle && pi >= 0;
     if (__any_sync(full, done)) {
       bool hit = false;
@@ -747,7 +748,7 @@ int launch(izpi_ctx* ctx, cudaStream_t st, K kern, dim3 grid, dim3 block, size_t
 }
 
 struct LaunchCfg {
-  bool use_g4, use_g2;
+  bool use_g4, use_g2, g2_deep;
   size_t smem, smem4, smem2;
   int ext_blocks, ext4_blocks, ext2_blocks;
 };
@@ -755,22 +756,26 @@ struct LaunchCfg {
 int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
   lc.smem = (size_t)kStackDepth * kThreads * sizeof(int32_t);
   lc.smem4 = (size_t)(kThreads / 4) * kG4Slab * sizeof(int2);
-  lc.smem2 = (size_t)(kExt2Threads / 2) * G2Slab<kG2Stack>::kSlots * sizeof(int2);
-  static thread_local int ext_blocks = 0, ext4_blocks = 0, ext2_blocks = 0;
+  lc.g2_deep = ctx->scene.g4_need > kG2Stack;  // the 52-entry slab (intersect_g2.cuh)
+  const size_t smem2_a = (size_t)(kExt2Threads / 2) * G2Slab<kG2Stack>::kSlots * sizeof(int2);
+  const size_t smem2_b = (size_t)(kExt2Threads / 2) * G2Slab<kG2StackDeep>::kSlots * sizeof(int2);
+  lc.smem2 = lc.g2_deep ? smem2_b : smem2_a;
+  static thread_local int ext_blocks = 0, ext4_blocks = 0, ext2_blocks_a = 0, ext2_blocks_b = 0;
   if (!ext_blocks) {
-    IZ_CUDA(cudaFuncSetAttribute(extend_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem2));
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext2_blocks, extend_g2_kernel, kExt2Threads, lc.smem2));
-    if (ext2_blocks < 1) ext2_blocks = 1;
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext2_blocks_a, extend_g2_kernel<kG2Stack>, kExt2Threads, smem2_a));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext2_blocks_b, extend_g2_kernel<kG2StackDeep>, kExt2Threads, smem2_b));
+    if (ext2_blocks_a < 1) ext2_blocks_a = 1;
+    if (ext2_blocks_b < 1) ext2_blocks_b = 1;
     IZ_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_blocks, extend_kernel, kThreads, lc.smem));
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext4_blocks, extend_g4_kernel, kThreads, lc.smem4));
     if (ext_blocks < 1) ext_blocks = 1;
     if (ext4_blocks < 1) ext4_blocks = 1;
   }
-  lc.ext_blocks = ext_blocks; lc.ext4_blocks = ext4_blocks; lc.ext2_blocks = ext2_blocks;
+  lc.ext_blocks = ext_blocks; lc.ext4_blocks = ext4_blocks; lc.ext2_blocks = lc.g2_deep ? ext2_blocks_b : ext2_blocks_a;
   // tiny trees (config 4 has 22 primitives) stay cache-resident and coherent: the thread-per-ray stage wins there
   lc.use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= 64;
-  lc.use_g2 = lc.use_g4 && ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2Stack;
+  lc.use_g2 = lc.use_g4 && ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2StackDeep;
   return IZPI_OK;
 }
 
@@ -810,7 +815,7 @@ int batch_step(izpi_ctx* ctx, RenderState* r, BatchSlot& s, const LaunchCfg& lc)
   if (lc.use_g2) {
     long long want2 = ((long long)s.live + (kExt2Threads / 2) - 1) / (kExt2Threads / 2);
     int eg2 = (int)std::max<long long>(1, std::min<long long>(want2, (long long)sm * lc.ext2_blocks));
-    if ((rc = launch(ctx, st, extend_g2_kernel, dim3(eg2), dim3(kExt2Threads), lc.smem2, ctx->scene, r->rp, s.d_paths, s.q,
+    if ((rc = launch(ctx, st, lc.g2_deep ? extend_g2_kernel<kG2StackDeep> : extend_g2_kernel<kG2Stack>, dim3(eg2), dim3(kExt2Threads), lc.smem2, ctx->scene, r->rp, s.d_paths, s.q,
                      ctx->pair_stragglers)) != IZPI_OK) return rc;
   } else if (lc.use_g4) {
     long long want4 = ((long long)s.live + (kThreads / 4) - 1) / (kThreads / 4);

@@ -304,13 +304,14 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
   if (n > (1ll << 30)) { set_error("izpi_trace_closest: at most 2^30 rays per launch; split the batch"); return IZPI_EINVAL; }
   IZ_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), st));
   // Two lanes per ray (16 rays per warp) when the tree's worst-case stack fits the kG2Stack-entry slab (six resident
-  // blocks x 64 rays x 464 B of shared memory); with the reference's full 64 entries only five blocks would fit, and the
+  // blocks x 32 rays x 464 B of shared memory, or 13 x 32 x 496 B for the 52-entry variant); with the reference's full 64 entries only five blocks would fit, and the
   // 4-lane kernel (8 rays per warp, 7 blocks) is faster than that.  NewBVH4 trees are balanced -- three entries per level
   // of inner nodes: 27 for the 1 M-triangle mesh, 33 for 11.5 M -- so they fit; a tree that does not is still traced
   // exactly, by the 4-lane kernel.
   if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && (!ctx->force_scalar || mode == IZPI_TRACE_FP32) &&
-      ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2Stack) {
-    return launch_g2<kG2Stack>(ctx, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, st, count, counters);
+      ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2StackDeep) {
+    if (ctx->scene.g4_need <= kG2Stack) return launch_g2<kG2Stack>(ctx, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, st, count, counters);
+    return launch_g2<kG2StackDeep>(ctx, n, d_org, d_dir, tmin, tmax, mode, d_ids, d_t, st, count, counters);
   }
   if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && (!ctx->force_scalar || mode == IZPI_TRACE_FP32)) {
     size_t smem4 = (size_t)(kTraceThreads / 4) * kG4Slab * sizeof(int2);
