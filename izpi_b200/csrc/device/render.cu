@@ -460,7 +460,16 @@ __device__ __forceinline__ d3 dielectric_common(const DRay& r, const DHit& h, Rn
 }
 
 template <int CLS>
-__global__ void __launch_bounds__(kThreads)
+// Resident blocks per SM: without a bound the dielectric class takes 158 registers (3 blocks) and the others up to 118 (4);
+// capping them at 128 / 96 registers spills a little but the extra warps win (config 4: 87 -> 96 Msamples/s with 4 blocks
+// for the dielectric class; config 1: 401 -> 431 with 5 blocks for the others).
+#ifndef IZPI_SHADE_MIN_BLOCKS_DIELECTRIC
+#define IZPI_SHADE_MIN_BLOCKS_DIELECTRIC 4
+#endif
+#ifndef IZPI_SHADE_MIN_BLOCKS
+#define IZPI_SHADE_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(kThreads, (CLS == IZPI_MAT_DIELECTRIC ? IZPI_SHADE_MIN_BLOCKS_DIELECTRIC : IZPI_SHADE_MIN_BLOCKS))
 shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q) {
   const long long n = (long long)q.counters[2 + CLS];
   const int32_t* bin = q.bins + (size_t)CLS * q.capacity;
