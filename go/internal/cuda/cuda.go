@@ -21,7 +21,7 @@ import (
 	"unsafe"
 )
 
-// Context is one GPU.
+// Context is one GPU, or a group of GPUs of one box driven by one host thread per GPU inside the library (NewGroup).
 type Context struct{ h *C.izpi_ctx }
 
 func lastError(op string, rc C.int) error {
@@ -34,6 +34,22 @@ func NewContext(dev int) (*Context, error) {
 	id := C.int(dev)
 	var h *C.izpi_ctx
 	if rc := C.izpi_ctx_create(1, &id, &h); rc != 0 {
+		return nil, lastError("izpi_ctx_create", rc)
+	}
+	return &Context{h: h}, nil
+}
+
+// NewGroup opens all of `devs` as ONE context: the scene is flattened once and copied device-to-device, ray batches are
+// split, tiles are claimed dynamically from one cursor and RenderFinish merges the members' disjoint tiles.  This is the
+// drop-in for RendererImpl.Render's worker pool (renderer.go:126-147) on a multi-GPU box.
+func NewGroup(devs []int) (*Context, error) {
+	runtime.LockOSThread()
+	ids := make([]C.int, len(devs))
+	for i, d := range devs {
+		ids[i] = C.int(d)
+	}
+	var h *C.izpi_ctx
+	if rc := C.izpi_ctx_create(C.int(len(ids)), ptr(ids), &h); rc != 0 {
 		return nil, lastError("izpi_ctx_create", rc)
 	}
 	return &Context{h: h}, nil
@@ -54,7 +70,27 @@ type SceneDesc struct {
 	Spectral   []C.izpi_spectral_texture_spec
 	Camera     C.izpi_camera
 	HasWorld   bool
-	pin        runtime.Pinner // keeps texture pixel slices addressable during Upload
+	pin        runtime.Pinner // pins what the nested pointers of Textures / Spectral refer to (PinDoubles) until Upload returns
+}
+
+// PinDoubles pins a Go slice that a nested pointer of the descriptor (izpi_texture_spec.pixels,
+// izpi_spectral_texture_spec.wavelengths / values) refers to, and returns that pointer.  The cgo rules allow Go memory handed
+// to C to contain Go pointers only when their targets are pinned; Upload unpins everything when it returns.
+func (d *SceneDesc) PinDoubles(s []float64) *C.double {
+	if len(s) == 0 {
+		return nil
+	}
+	d.pin.Pin(&s[0])
+	return (*C.double)(&s[0])
+}
+
+// pinned returns the base pointer of s after pinning it in p (nil for an empty slice).
+func pinned[T any](p *runtime.Pinner, s []T) *T {
+	if len(s) == 0 {
+		return nil
+	}
+	p.Pin(&s[0])
+	return &s[0]
 }
 
 func ptr[T any](s []T) *T {
@@ -67,20 +103,24 @@ func ptr[T any](s []T) *T {
 // Upload copies the flattened scene to the GPU (replaces nothing in the reference: the CPU path keeps
 // its object graph; this is the additional one-off step after transport.ToScene()).
 func (c *Context) Upload(d *SceneDesc) error {
+	// cd lives in Go memory and holds Go pointers: every one of them is pinned for the duration of the call
+	// (runtime.Pinner, Go >= 1.21), which is what cgocheck requires of Go memory passed to C.
+	var p runtime.Pinner
+	defer p.Unpin()
+	defer d.pin.Unpin()
 	var cd C.izpi_scene_desc
 	cd.world_kind = C.int32_t(d.WorldKind)
-	cd.n_nodes, cd.nodes = C.int32_t(len(d.Nodes)), ptr(d.Nodes)
-	cd.n_prims, cd.prims, cd.tri_attrs = C.int32_t(len(d.Prims)), ptr(d.Prims), ptr(d.TriAttrs)
-	cd.n_xforms, cd.xforms = C.int32_t(len(d.Xforms)), ptr(d.Xforms)
-	cd.n_lights, cd.lights = C.int32_t(len(d.Lights)), (*C.int32_t)(unsafe.Pointer(ptr(d.Lights)))
-	cd.n_materials, cd.materials = C.int32_t(len(d.Materials)), ptr(d.Materials)
-	cd.n_textures, cd.textures = C.int32_t(len(d.Textures)), ptr(d.Textures)
-	cd.n_spectral_textures, cd.spectral_textures = C.int32_t(len(d.Spectral)), ptr(d.Spectral)
+	cd.n_nodes, cd.nodes = C.int32_t(len(d.Nodes)), pinned(&p, d.Nodes)
+	cd.n_prims, cd.prims, cd.tri_attrs = C.int32_t(len(d.Prims)), pinned(&p, d.Prims), pinned(&p, d.TriAttrs)
+	cd.n_xforms, cd.xforms = C.int32_t(len(d.Xforms)), pinned(&p, d.Xforms)
+	cd.n_lights, cd.lights = C.int32_t(len(d.Lights)), (*C.int32_t)(unsafe.Pointer(pinned(&p, d.Lights)))
+	cd.n_materials, cd.materials = C.int32_t(len(d.Materials)), pinned(&p, d.Materials)
+	cd.n_textures, cd.textures = C.int32_t(len(d.Textures)), pinned(&p, d.Textures)
+	cd.n_spectral_textures, cd.spectral_textures = C.int32_t(len(d.Spectral)), pinned(&p, d.Spectral)
 	cd.camera = d.Camera
 	if d.HasWorld {
 		cd.dielectric_has_world = 1
 	}
-	defer d.pin.Unpin()
 	if rc := C.izpi_scene_upload(c.h, &cd); rc != 0 {
 		return lastError("izpi_scene_upload", rc)
 	}
@@ -124,8 +164,12 @@ func (c *Context) RenderSetup(rc RenderConfig) error {
 	for i := 0; i < 3; i++ {
 		cc.background[i] = C.double(rc.Background[i])
 	}
-	if len(rc.BgWavelengths) > 0 {
-		cc.bg_wavelengths, cc.bg_values, cc.n_bg = (*C.double)(&rc.BgWavelengths[0]), (*C.double)(&rc.BgValues[0]), C.int32_t(len(rc.BgWavelengths))
+	var p runtime.Pinner // cc holds Go pointers: pin their targets for the call
+	defer p.Unpin()
+	if len(rc.BgWavelengths) > 0 && len(rc.BgValues) == len(rc.BgWavelengths) {
+		cc.bg_wavelengths = (*C.double)(pinned(&p, rc.BgWavelengths))
+		cc.bg_values = (*C.double)(pinned(&p, rc.BgValues))
+		cc.n_bg = C.int32_t(len(rc.BgWavelengths))
 	}
 	cc.seed = C.uint64_t(rc.Seed)
 	if r := C.izpi_render_setup(c.h, &cc); r != 0 {
@@ -141,6 +185,19 @@ func (c *Context) RenderTiles(tiles []uint32) error {
 	}
 	if r := C.izpi_render_tiles(c.h, C.int32_t(len(tiles)/4), (*C.uint32_t)(&tiles[0]), nil); r != 0 {
 		return lastError("izpi_render_tiles", r)
+	}
+	return nil
+}
+
+// RenderTilesShared is RenderTiles over a tile list shared with other contexts: cursor (C memory, e.g. C.calloc(1, 8),
+// initially 0) is the index of the next unclaimed tile and every sharer claims runs of tiles from it -- the work-unit
+// channel of renderer.go:126-147.  sharers = number of contexts pulling from the cursor.
+func (c *Context) RenderTilesShared(tiles []uint32, cursor *C.uint64_t, sharers int) error {
+	if len(tiles) == 0 {
+		return nil
+	}
+	if r := C.izpi_render_tiles_shared(c.h, C.int32_t(len(tiles)/4), (*C.uint32_t)(&tiles[0]), cursor, C.int32_t(sharers), nil); r != 0 {
+		return lastError("izpi_render_tiles_shared", r)
 	}
 	return nil
 }

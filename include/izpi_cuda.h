@@ -47,9 +47,21 @@ typedef struct izpi_ctx izpi_ctx;
 const char* izpi_last_error(void);
 int izpi_version(void);
 
-/* One context per GPU.  n_devices must be 1 in this release: the process-per-GPU model
- * (one rank per device, NCCL through the host runtime) is the multi-GPU path. */
+/* A context drives one GPU or a GROUP of GPUs of one box (n_devices > 1, distinct device_ids; NULL = devices 0..n-1).
+ * The reference starts its N workers from ONE process and hands them work units from one channel
+ * (internal/render/renderer.go:126-147); a group does the same with one host thread per GPU inside the library:
+ *   izpi_scene_upload   flattens / validates once, uploads to the first device and copies every array to the other
+ *                       members device-to-device (cudaMemcpyPeerAsync, NVLink when the pair are peers);
+ *   izpi_trace_closest  cuts the ray batch into contiguous slices, one per member, answers land in disjoint host ranges;
+ *   izpi_render_tiles   deals the tiles DYNAMICALLY: every member claims the next run of tiles from one shared cursor
+ *                       whenever it has room for another batch (no static assignment, sky and mesh tiles balance out);
+ *   izpi_render_finish  merges: pixels are disjoint, so every member sends only the tiles it rendered (RGB / AOV samplers:
+ *                       straight into the caller's canvas, N device-to-host streams in parallel; spectral: to the first
+ *                       device, whose FireflyRejection needs the neighbours) -- no full-canvas reduction.
+ * Every other entry point (displacement, device BVH build, tile rows, diagnostics) runs on the first device.
+ * One process per GPU (one single-device context each, NCCL between them) remains possible: izpi_render_tiles_shared. */
 int izpi_ctx_create(int n_devices, const int* device_ids, izpi_ctx** out);
+int izpi_ctx_num_devices(const izpi_ctx* ctx);
 void izpi_ctx_destroy(izpi_ctx* ctx);
 
 /* ---- flattened scene ------------------------------------------------------------------
@@ -115,6 +127,20 @@ typedef struct izpi_scene_desc {
 
 int izpi_scene_upload(izpi_ctx* ctx, const izpi_scene_desc* desc);
 
+/* ---- scene image: replicate an uploaded scene without rebuilding it ---------------------------------------------------
+ * The reference ships the scene to every LAN worker, each of which re-runs ToScene() and NewBVH4
+ * (internal/transport/transport.go:53-92); on one NVLink box the flattened arrays are copied instead.  The uploaded
+ * scene is an ordered list of device blocks plus a small host header (sizes, pointer tables).  Exporter:
+ * izpi_scene_image_size, then izpi_scene_image_export (header bytes; per block its size and device pointer).  Importer:
+ * izpi_scene_image_adopt(header) allocates the same blocks on ITS device and returns their pointers, the caller fills
+ * them by any transport (cudaMemcpyPeerAsync inside a process -- what a device group does -- or an NCCL broadcast
+ * between one-process-per-GPU ranks), then izpi_scene_image_commit re-bases the pointer tables.  The header is opaque
+ * and only valid between contexts of the same library build. */
+int izpi_scene_image_size(izpi_ctx* src, uint64_t* header_bytes, int32_t* n_blocks);
+int izpi_scene_image_export(izpi_ctx* src, void* header, uint64_t* block_bytes, void** d_blocks);
+int izpi_scene_image_adopt(izpi_ctx* dst, const void* header, uint64_t header_bytes, void** d_blocks_out);
+int izpi_scene_image_commit(izpi_ctx* dst);
+
 /* ---- closest hit ------------------------------------------------------------------------ */
 #define IZPI_TRACE_EXACT 0 /* reference traversal order, fp32 SSE-flavour box test, fp64 primitives: bit-exact */
 #define IZPI_TRACE_FP32 1  /* optional: fp32 primitive tests, reported separately (not parity-checked bitwise) */
@@ -173,12 +199,20 @@ int izpi_debug_fma_peak(izpi_ctx* ctx, int fp64, double* tflops);
 #define IZPI_SAMPLER_ALBEDO 2   /* sampler/albedo.go: material albedo at the first hit, black on a miss */
 #define IZPI_SAMPLER_NORMAL 3   /* sampler/normal.go: hit-record normal at the first hit */
 
+/* izpi_render_config.flags: measurement modes; the image is unchanged.  Results: izpi_render_get_stats.
+ *   IZPI_RENDER_TIMING  CUDA events around every stage of every bounce, with ONE batch in flight instead of two so that a
+ *                       stage's time is its own (the frame is slower by the lost overlap);
+ *   IZPI_RENDER_STATS   the same plus counting variants of the extend kernels: nodes visited / primitive tests, the
+ *                       counters of izpi_trace_stats (a few per cent slower than the plain kernels). */
+#define IZPI_RENDER_STATS 1
+#define IZPI_RENDER_TIMING 2
+
 typedef struct izpi_render_config {
   int32_t width, height, spp, max_depth;
   int32_t sampler;
   int32_t sample_offset; /* first global sample index rendered by this context (sample-range sharding) */
   int32_t sample_count;  /* samples of every pixel rendered by this context; the mean still divides by spp */
-  int32_t reserved;
+  int32_t flags;         /* IZPI_RENDER_* bits; 0 for production renders */
   double background[3];        /* colours.Black by default */
   const double* bg_wavelengths; /* spectral background SPD (control.proto:64-67); NULL = SpectralBlack */
   const double* bg_values;
@@ -193,6 +227,15 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg);
  * NULL the rendered tiles' pixels are also written there (4*W*H doubles, Float64NRGBA layout,
  * reference row flip rgb.go:41). */
 int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* x0y0x1y1, double* canvas_rgba);
+/* The same for a tile list SHARED with other contexts: *cursor (initially 0) is the index of the next unclaimed tile; every
+ * sharer passes the same list and the same cursor and claims runs of tiles from it with atomic fetch-adds until the list is
+ * exhausted, the way the reference's workers pull work units from one channel (renderer.go:126-147).  `sharers` = how many
+ * contexts pull from the cursor (sizes the claims: guided self-scheduling, large runs first, short ones at the end).  The
+ * cursor may live in memory shared between processes (one process per GPU).  Each context's canvas then holds the sums of
+ * the tiles it claimed and zeros elsewhere, so the merge is a sum (NCCL reduce) or a gather of disjoint pixels.  A device
+ * group uses this internally; cursor = NULL is izpi_render_tiles. */
+int izpi_render_tiles_shared(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* x0y0x1y1, uint64_t* cursor, int32_t sharers,
+                             double* canvas_rgba);
 /* worker.RenderTile (internal/worker/render.go:17-75; RenderTileRequest/Response, internal/proto/control/control.proto:75-89):
  * renders ONE tile and returns what the worker streams back, row by row: (y1-y0+1) rows, row r = image row y0 + r (the
  * worker does not flip; the leader places it at ny - pos_y, render/remote.go:63-69), each row strip_height*4*(x1-x0+1)
@@ -203,8 +246,21 @@ int izpi_render_tile_rows(izpi_ctx* ctx, uint32_t strip_height, uint32_t x0, uin
 /* Device pointer of the context's canvas accumulator (4*W*H doubles: per-pixel SUMS over the
  * samples rendered so far, alpha = 1 where written) so that the host runtime can ncclReduce it. */
 int izpi_render_canvas_device(izpi_ctx* ctx, double** d_canvas);
-/* Divide by spp, apply the epilogue (spectral: FireflyRejection + XYZ->ACEScg), copy to host. */
+/* Divide by spp, apply the epilogue (spectral: FireflyRejection + XYZ->ACEScg), copy to host.  For a device group this
+ * is also the merge of the members' disjoint tiles (see izpi_ctx_create). */
 int izpi_render_finish(izpi_ctx* ctx, double* canvas_rgba, uint64_t* total_rays);
+
+/* Totals since the last izpi_render_setup.  `rays` is always filled (the reference's numRays, colour.go:38); the visit /
+ * test counts and the stage times need IZPI_RENDER_STATS.  Algorithmic bytes of the extend stage:
+ * 128 * nodes_visited + 72 * prim_tests + 60 * rays.  For a device group: counts are summed, times are the slowest member's. */
+typedef struct izpi_render_stats {
+  uint64_t rays, nodes_visited, prim_tests;
+  uint64_t extend_launches;
+  double extend_ms; /* summed device time of the extend (closest-hit) launches */
+  double shade_ms;  /* ... of the shade launches + queue advance */
+  double other_ms;  /* ... of ray generation and resolve */
+} izpi_render_stats;
+int izpi_render_get_stats(izpi_ctx* ctx, izpi_render_stats* out);
 
 #ifdef __cplusplus
 }

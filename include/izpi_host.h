@@ -39,6 +39,15 @@ int izpi_host_scene_upload(const izpi_host_scene* s, izpi_ctx* ctx);
 /* common.Tiles (common/tiles.go:6-24); 0 when no listed size divides the dimension. */
 void izpi_host_tiles(int32_t size_x, int32_t size_y, int32_t* step_x, int32_t* step_y);
 
+/* The claim policy of a shared tile cursor (izpi_render_tiles_shared): guided self-scheduling.  A claimer with room for
+ * one more batch takes (tiles left) / (2 * takers) tiles, at most one full batch (batch_paths / tile_paths tiles) and at
+ * least 2^20 paths' worth (smaller batches are launch-bound), with one atomic fetch-add on *cursor; takers = contexts x
+ * batches in flight per context.  takers <= 1 (a private cursor) claims everything at once.  Returns 0 when the list is
+ * exhausted, else 1 with the claimed range [*begin, *end).  Pure host code: the cursor may sit in memory shared between
+ * processes.  Mirrors the work-unit channel of renderer.go:126-147. */
+int izpi_host_claim_tiles(uint64_t* cursor, int32_t n_tiles, int64_t tile_paths, int64_t batch_paths, int32_t takers,
+                          int32_t* begin, int32_t* end);
+
 /* RendererImpl.Render (renderer.go:108-222) for the local path on one context: tile grid from
  * common.Tiles, tiles [tile_begin, tile_end) of the row-major grid submitted in batches, then
  * izpi_render_finish when `finish` is set.  tile_end = -1 means all tiles. */

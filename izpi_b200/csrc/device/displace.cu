@@ -152,9 +152,23 @@ void displace_result_free(izpi_ctx* ctx) {
   ctx->displace = nullptr;
 }
 
-extern "C" {
+namespace {
 
-int izpi_displace(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t* materials, int32_t tex_w, int32_t tex_h,
+// Working buffers of one izpi_displace call.  Owned here so that EVERY exit path -- in particular the IZ_CUDA early returns
+// in the middle of a GB-scale tessellation -- releases them.
+struct DisplaceWork {
+  double* d_pix = nullptr;
+  DTri *d_in = nullptr, *d_next = nullptr, *d_child = nullptr, *d_done = nullptr;
+  int32_t *d_flag = nullptr, *d_pos = nullptr;
+  void* d_tmp = nullptr;
+  int32_t *d_k0 = nullptr, *d_k1 = nullptr, *d_v0 = nullptr, *d_v1 = nullptr;
+  ~DisplaceWork() {
+    cudaFree(d_pix); cudaFree(d_in); cudaFree(d_next); cudaFree(d_child); cudaFree(d_done); cudaFree(d_flag); cudaFree(d_pos); cudaFree(d_tmp);
+    cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_v0); cudaFree(d_v1);
+  }
+};
+
+int displace_impl(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t* materials, int32_t tex_w, int32_t tex_h,
                   const double* pixels_rgba, double mn, double mx, int per_triangle, int64_t* n_out) {
   if (!ctx || n < 0 || (n > 0 && !tris15) || !pixels_rgba || tex_w < 2 || tex_h < 2 || !n_out || n > (1 << 28)) {
     set_error("izpi_displace: bad argument (the displacement map must be an image of at least 2x2 texels)");
@@ -174,24 +188,24 @@ int izpi_displace(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t*
     h_in[i].mat = materials ? materials[i] : 0;
     h_in[i].base = (int32_t)i;
   }
-  double* d_pix = nullptr;
+  DisplaceWork w;
+  double*& d_pix = w.d_pix;
   IZ_CUDA(cudaMalloc(&d_pix, (size_t)tex_w * tex_h * 32));
   IZ_CUDA(cudaMemcpyAsync(d_pix, pixels_rgba, (size_t)tex_w * tex_h * 32, cudaMemcpyHostToDevice, st));
   DispMap m{d_pix, tex_w, tex_h, mn, mx, 4.0 / (double)(tex_w - 1), 4.0 / (double)(tex_h - 1)};  // displacement.go:176-178
-  DTri *d_in = nullptr, *d_next = nullptr, *d_child = nullptr, *d_done = nullptr;
-  int32_t *d_flag = nullptr, *d_pos = nullptr;
-  void* d_tmp = nullptr;
+  DTri *&d_in = w.d_in, *&d_next = w.d_next, *&d_child = w.d_child, *&d_done = w.d_done;
+  int32_t *&d_flag = w.d_flag, *&d_pos = w.d_pos;
+  void*& d_tmp = w.d_tmp;
   size_t cap_in = 0, cap_next = 0, cap_child = 0, cap_done = 0, cap_flag = 0, cap_pos = 0, cap_tmp = 0;
   int rc;
-  auto cleanup = [&]() { cudaFree(d_pix); cudaFree(d_in); cudaFree(d_next); cudaFree(d_child); cudaFree(d_done); cudaFree(d_flag); cudaFree(d_pos); cudaFree(d_tmp); };
-  if ((rc = grow(&d_in, &cap_in, (size_t)n, 0, st)) != IZPI_OK) { cleanup(); return rc; }
+  if ((rc = grow(&d_in, &cap_in, (size_t)n, 0, st)) != IZPI_OK) return rc;  // ~DisplaceWork releases everything
   IZ_CUDA(cudaMemcpyAsync(d_in, h_in.data(), (size_t)n * sizeof(DTri), cudaMemcpyHostToDevice, st));
   long long n_in = n, n_done = 0;
   for (int level = 0; n_in > 0; level++) {
-    if (level > 40 || 4 * n_in > (1ll << 30)) { cleanup(); set_error("izpi_displace: subdivision does not terminate / too many triangles"); return IZPI_EINVAL; }
+    if (level > 40 || 4 * n_in > (1ll << 30)) { set_error("izpi_displace: subdivision does not terminate / too many triangles"); return IZPI_EINVAL; }
     long long nc = 4 * n_in;
     if ((rc = grow(&d_child, &cap_child, (size_t)nc, 0, st)) != IZPI_OK || (rc = grow(&d_flag, &cap_flag, (size_t)nc, 0, st)) != IZPI_OK ||
-        (rc = grow(&d_pos, &cap_pos, (size_t)nc, 0, st)) != IZPI_OK) { cleanup(); return rc; }
+        (rc = grow(&d_pos, &cap_pos, (size_t)nc, 0, st)) != IZPI_OK) return rc;  // ~DisplaceWork releases everything
     tessellate_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(d_in, n_in, d_child, d_flag, m);
     ctx->launches++;
     size_t tmp_bytes = 0;
@@ -205,7 +219,7 @@ int izpi_displace(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t*
     IZ_CUDA(cudaStreamSynchronize(st));
     long long n_ok = (long long)last_pos + last_flag, n_todo = nc - n_ok;
     if ((rc = grow(&d_done, &cap_done, (size_t)(n_done + n_ok), (size_t)n_done, st)) != IZPI_OK ||
-        (rc = grow(&d_next, &cap_next, (size_t)std::max<long long>(n_todo, 1), 0, st)) != IZPI_OK) { cleanup(); return rc; }
+        (rc = grow(&d_next, &cap_next, (size_t)std::max<long long>(n_todo, 1), 0, st)) != IZPI_OK) return rc;  // ~DisplaceWork releases everything
     scatter_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(d_child, d_flag, d_pos, nc, d_done, n_done, d_next);
     ctx->launches++;
     IZ_CUDA(cudaGetLastError());
@@ -215,7 +229,7 @@ int izpi_displace(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t*
   }
   // order: as produced (levels, parents, children) or regrouped by input triangle (stable sort)
   int32_t* d_order = nullptr;
-  int32_t *d_k0 = nullptr, *d_k1 = nullptr, *d_v0 = nullptr, *d_v1 = nullptr;
+  int32_t *&d_k0 = w.d_k0, *&d_k1 = w.d_k1, *&d_v0 = w.d_v0, *&d_v1 = w.d_v1;
   if (per_triangle && n_done > 0 && n > 1) {
     IZ_CUDA(cudaMalloc(&d_k0, (size_t)n_done * 4)); IZ_CUDA(cudaMalloc(&d_k1, (size_t)n_done * 4));
     IZ_CUDA(cudaMalloc(&d_v0, (size_t)n_done * 4)); IZ_CUDA(cudaMalloc(&d_v1, (size_t)n_done * 4));
@@ -238,9 +252,21 @@ int izpi_displace(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t*
   IZ_CUDA(cudaStreamSynchronize(st));
   res->n = n_done;
   *n_out = n_done;
-  cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_v0); cudaFree(d_v1);
-  cleanup();
   return IZPI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int izpi_displace(izpi_ctx* ctx, int64_t n, const double* tris15, const int32_t* materials, int32_t tex_w, int32_t tex_h,
+                  const double* pixels_rgba, double mn, double mx, int per_triangle, int64_t* n_out) {
+  int rc = displace_impl(ctx, n, tris15, materials, tex_w, tex_h, pixels_rgba, mn, mx, per_triangle, n_out);
+  if (rc != IZPI_OK && ctx) {  // no half-built result: a later izpi_displace_fetch must fail, not return n = 0
+    cudaSetDevice(ctx->device);
+    displace_result_free(ctx);
+  }
+  return rc;
 }
 
 int izpi_displace_fetch(izpi_ctx* ctx, double* out_tris15, int32_t* out_materials) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,8 @@ struct DScene {
   int32_t g4_ok;                // nodes_t is usable (reference-shaped tree: leaves are own slot-0-only nodes)
   int32_t root_is_leaf;
   int32_t g4_need;              // most stack entries a ray can need in THIS tree (<= 64, bvh4.go:71); picks the slab size of the 2-lane kernel
+  int32_t class_mask;           // bit c set <=> some primitive carries a material of class c (IZPI_MAT_*): shade launches of absent classes are skipped
+  int32_t n_textures, n_spectex;
   const float4* nodes;          // 8 x float4 per BVH4Node, verbatim SoA layout, 128-B aligned
   const float4* nodes_t;        // child-major copy: 4 x {minx miny minz maxx | maxy maxz ref cnt}, leaf-nodes folded in, empty slots NaN (context.cu)
   const izpi_prim_rec* prims;   // 80-B records in world order, 16-B aligned
@@ -56,6 +59,20 @@ struct DScene {
 
 struct RenderState;  // render.cu
 
+namespace izpi {
+// One cudaMalloc'ed piece of the uploaded scene.  The scene in HBM is the ordered list of these blocks plus the pointer
+// tables that refer into them (DScene, the texture tables); that is what izpi_scene_image_* ships to another device.
+struct SceneBlock {
+  void* d;
+  size_t bytes;
+};
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor results, per CONTEXT (= per device): 0 = not asked yet
+struct OccupancyCache {
+  int trace_g2[2] = {0, 0}, trace_g4 = 0, trace_scalar = 0;
+  int ext = 0, ext4 = 0, ext2[2] = {0, 0}, small = 0;
+};
+}  // namespace izpi
+
 struct izpi_ctx {
   int device = 0;
   int sm_count = 148;
@@ -67,7 +84,12 @@ struct izpi_ctx {
   int trace_lanes = 2;        // IZPI_TRACE_LANES=2|4: lanes per ray of izpi_trace_closest
   bool force_scalar = false;  // IZPI_FORCE_SCALAR=1: thread-per-ray traversal even for reference-shaped trees
   izpi::DScene scene{};
-  std::vector<void*> scene_allocs;  // freed on re-upload / destroy
+  std::vector<izpi::SceneBlock> scene_blocks;         // freed on re-upload / destroy
+  std::vector<izpi::DTexture> h_textures;             // host mirrors of the two pointer tables (re-based by izpi_scene_image_commit)
+  std::vector<izpi::DSpectralTexture> h_spectex;
+  std::vector<izpi::SceneBlock> adopt_src;            // izpi_scene_image_adopt: the exporter's block table, until commit
+  bool cie_uploaded = false;  // c_cie lives in __constant__ memory, which is per device: tracked per context
+  izpi::OccupancyCache occ;
   // trace scratch (grown on demand)
   double* d_org = nullptr; double* d_dir = nullptr; int32_t* d_ids = nullptr; double* d_t = nullptr;
   int64_t ray_capacity = 0;
@@ -77,4 +99,14 @@ struct izpi_ctx {
   RenderState* render = nullptr;
   void* displace = nullptr;  // result of the last izpi_displace (displace.cu)
   void* bvh_build = nullptr;  // result of the last izpi_bvh4_build (bvh_build.cu)
+  // Device group (izpi_ctx_create with n_devices > 1): this context is the group's first device; `subs` are single-device
+  // contexts for device_ids[1..].  Scene uploads are replicated device-to-device, ray batches and tiles are split across
+  // the members by one host thread per device (group.cpp-style code in context.cu / render.cu / trace.cu).
+  std::vector<izpi_ctx*> subs;
+  uint64_t group_cursor = 0;  // shared tile cursor of the group's current izpi_render_tiles call
 };
+
+namespace izpi {
+// context.cu: fn(member, index) on one host thread per member of the device group (inline for a single device)
+int group_run(izpi_ctx* ctx, const std::function<int(izpi_ctx*, int)>& fn);
+}  // namespace izpi

@@ -13,7 +13,9 @@
 // rgb.go:30-39) into the fp64 canvas.  All arithmetic is fp64 without FMA.
 #include <algorithm>
 #include <cstring>
+#include <deque>
 
+#include "../../../include/izpi_host.h"
 #include "intersect_g2.cuh"
 #include "shade.cuh"
 
@@ -52,7 +54,7 @@ struct Queues {
   int32_t* cur;                 // live paths entering this bounce
   int32_t* next;                // survivors
   int32_t* bins;                // [kClasses][capacity]
-  unsigned long long* counters; // [0] cur count, [1] next count, [2..6] bin counts, [7] work head, [8] rays traced
+  unsigned long long* counters; // [0] cur count, [1] next count, [2..6] bin counts, [7] work head, [8] rays traced, [9] nodes visited, [10] primitive tests (counting kernels)
   int32_t capacity;
 };
 
@@ -159,6 +161,7 @@ __device__ __forceinline__ d3 background_term(const RenderParams& rp, double lam
 }
 
 // ---- extend ---------------------------------------------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(kThreads)
 extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q) {
   extern __shared__ int32_t stack_smem[];
@@ -188,7 +191,7 @@ extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* pat
         traced++;  // atomic.AddUint64(numRays, 1) (colour.go:38)
         DRay r = path_ray(p);
         double t = 0;
-        int rec = world_closest<false>(sc, r, 0.001, DBL_MAX, t, stack, kThreads, nn, np);
+        int rec = world_closest<COUNT>(sc, r, 0.001, DBL_MAX, t, stack, kThreads, nn, np);
         if (rec < 0) {
           d3 beta = mk(p.bx, p.by, p.bz), acc = mk(p.ax, p.ay, p.az);
           finish_path(rp, p, acc + hadamard(beta, background_term(rp, p.lambda)));
@@ -203,12 +206,14 @@ extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* pat
     push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + 2);
   }
   if (traced) atomicAdd(&q.counters[8], traced);
+  if (COUNT) { atomicAdd(&q.counters[9], (unsigned long long)nn); atomicAdd(&q.counters[10], (unsigned long long)np); }
 }
 
 // Same stage with the 4-lanes-per-ray traversal (intersect_g4.cuh) for reference-shaped BVH4 worlds:
 // 8 paths per warp, queue indices drawn in chunks, finished groups replaced immediately.
 constexpr int kExtendChunk = 256;
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, 7)  // 72 registers: seven resident blocks per SM (latency-bound kernel; 8 gains nothing, trace.cu)
 extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q, int stragglers) {
   extern __shared__ int2 g4_stack_smem[];
@@ -258,8 +263,8 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
       chunk_next += take < total ? take : total;
       if (exhausted && __ballot_sync(full, s.cur == kIdle && pi < 0) == full) break;
     }
-    g4_node_phase<false>(s, sc, stack, lane, gshift, j, nn, stragglers);
-    g4_leaf_phase<false>(s, sc, stack, lane, gshift, j, nn, np, 0.001);
+    g4_node_phase<COUNT>(s, sc, stack, lane, gshift, j, nn, stragglers);
+    g4_leaf_phase<COUNT>(s, sc, stack, lane, gshift, j, nn, np, 0.001);
     const bool done = s.cur == kIdle && pi >= 0;
     if (__any_sync(full, done)) {
       bool hit = false;
@@ -279,6 +284,10 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
     }
   }
   if (traced) atomicAdd(&q.counters[8], (unsigned long long)traced);
+  if (COUNT) {  // nodes are counted by the first lane of a ray's group, primitive tests by the lane that ran them (trace.cu)
+    if (j == 0) atomicAdd(&q.counters[9], (unsigned long long)nn);
+    atomicAdd(&q.counters[10], (unsigned long long)np);
+  }
 }
 
 
@@ -289,7 +298,7 @@ constexpr int kExt2Threads = 64;  // two-warp blocks, 14 per SM at 72 registers 
 #ifndef IZPI_EXT2_MIN_BLOCKS
 #define IZPI_EXT2_MIN_BLOCKS 14
 #endif
-template <int STACK>
+template <int STACK, bool COUNT>
 __global__ void __launch_bounds__(kExt2Threads, IZPI_EXT2_MIN_BLOCKS)
 extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q, int stragglers) {
   extern __shared__ int2 g4_stack_smem[];
@@ -344,8 +353,8 @@ extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
       chunk_next += take < total ? take : total;
       if (exhausted && __ballot_sync(full, s.cur == kIdle && pi < 0) == full) break;
     }
-    g2_node_phase<false, STACK>(s, sc, stack, pshift, j, nn, stragglers);
-    g2_leaf_phase<false, false, STACK>(s, sc, stack, pshift, j, nn, np, 0.001);
+    g2_node_phase<COUNT, STACK>(s, sc, stack, pshift, j, nn, stragglers);
+    g2_leaf_phase<COUNT, false, STACK>(s, sc, stack, pshift, j, nn, np, 0.001);
     const bool done = s.cur == kIdle && pi >= 0;
     if (__any_sync(full, done)) {
       bool hit = false;
@@ -365,6 +374,10 @@ extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
     }
   }
   if (traced) atomicAdd(&q.counters[8], (unsigned long long)traced);
+  if (COUNT) {  // nodes are counted by the first lane of a ray's group, primitive tests by the lane that ran them (trace.cu)
+    if (j == 0) atomicAdd(&q.counters[9], (unsigned long long)nn);
+    atomicAdd(&q.counters[10], (unsigned long long)np);
+  }
 }
 
 // ---- shade ----------------------------------------------------------------------------------
@@ -686,10 +699,17 @@ __global__ void xyz_to_acescg_kernel(double* pix, long long n_px, double exposur
 // nearly empty bounces (paths caught between glass and metal live up to maxDepth = 50 bounces), the next
 // one fills the SMs with its first, wide bounces.  Resolves are chained in batch order, so every pixel
 // still adds its samples in the reference's order and the canvas is independent of the overlap.
+//
+// Where the tiles come from: a CURSOR over the caller's tile list.  A context that shares the list with other
+// contexts (the members of a device group, or one-process-per-GPU ranks with the cursor in shared memory) claims the
+// next run of tiles with one atomic fetch-add whenever a slot has room -- the reference's workers pull work units from
+// one channel the same way (renderer.go:126-147) -- so nobody is handed a fixed share of cheap sky tiles or dear mesh tiles.
 constexpr int kSlots = 2;
 constexpr int kMaxBounces = 4096;
 
-__global__ void accumulate_traced_kernel(const unsigned long long* counters, unsigned long long* total) { *total += counters[8]; }
+__global__ void accumulate_traced_kernel(const unsigned long long* counters, unsigned long long* total) {
+  total[0] += counters[8]; total[1] += counters[9]; total[2] += counters[10];
+}
 
 struct BatchSlot {
   PathState* d_paths = nullptr;
@@ -707,6 +727,8 @@ struct BatchSlot {
   unsigned long long live = 0;
 };
 
+struct TileRun { uint32_t x0, y0, x1, y1; };  // horizontally merged tiles rendered by this context since the last setup
+
 struct RenderState {
   izpi_render_config cfg{};
   RenderParams rp{};
@@ -715,10 +737,20 @@ struct RenderState {
   double* d_snap = nullptr;
   size_t canvas_capacity = 0;
   double* d_bg = nullptr;
-  unsigned long long* d_total_rays = nullptr;
+  unsigned long long* d_total_rays = nullptr;  // [0] rays traced, [1] nodes visited, [2] primitive tests (counting kernels)
   BatchSlot slot[kSlots];
   int32_t batch_paths = 1 << 24;  // paths per batch: 16M x 160 B = 2.7 GB of HBM per slot
   bool allocated = false;
+  std::vector<TileRun> rendered;  // what izpi_render_finish of a device group has to move
+  long long rendered_pixels = 0;
+  // IZPI_RENDER_STATS: per-stage CUDA-event time (batches serialised) and counting extend kernels
+  bool stats_on = false;  // events around the stages, one batch in flight
+  bool count_on = false;  // counting extend kernels
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { cudaEvent_t a, b; int kind; };  // kind 0 extend, 1 shade + advance, 2 raygen / resolve
+  std::vector<Span> spans;
+  izpi_render_stats stats{};
 };
 
 void render_state_free(izpi_ctx* ctx) {
@@ -732,6 +764,7 @@ void render_state_free(izpi_ctx* ctx) {
     if (s.resolved) cudaEventDestroy(s.resolved);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  for (cudaEvent_t e : r->ev_pool) cudaEventDestroy(e);
   delete r;
   ctx->render = nullptr;
 }
@@ -740,11 +773,12 @@ namespace {
 
 #include "cie_tables.inc"
 
-int upload_cie() {
-  static thread_local bool done = false;
-  if (done) return IZPI_OK;
+// c_cie is __constant__ memory: one copy per DEVICE, so the upload is tracked per context (a thread that owns contexts on
+// two GPUs must fill both)
+int upload_cie(izpi_ctx* ctx) {
+  if (ctx->cie_uploaded) return IZPI_OK;
   IZ_CUDA(cudaMemcpyToSymbol(c_cie, kCieTable, sizeof(kCieTable)));
-  done = true;
+  ctx->cie_uploaded = true;
   return IZPI_OK;
 }
 
@@ -757,7 +791,7 @@ int launch(izpi_ctx* ctx, cudaStream_t st, K kern, dim3 grid, dim3 block, size_t
 }
 
 struct LaunchCfg {
-  bool use_g4, use_g2, g2_deep;
+  bool use_g4, use_g2, g2_deep, count;
   size_t smem, smem4, smem2;
   int ext_blocks, ext4_blocks, ext2_blocks;
 };
@@ -769,22 +803,44 @@ int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
   const size_t smem2_a = (size_t)(kExt2Threads / 2) * G2Slab<kG2Stack>::kSlots * sizeof(int2);
   const size_t smem2_b = (size_t)(kExt2Threads / 2) * G2Slab<kG2StackDeep>::kSlots * sizeof(int2);
   lc.smem2 = lc.g2_deep ? smem2_b : smem2_a;
-  static thread_local int ext_blocks = 0, ext4_blocks = 0, ext2_blocks_a = 0, ext2_blocks_b = 0;
-  if (!ext_blocks) {
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext2_blocks_a, extend_g2_kernel<kG2Stack>, kExt2Threads, smem2_a));
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext2_blocks_b, extend_g2_kernel<kG2StackDeep>, kExt2Threads, smem2_b));
-    if (ext2_blocks_a < 1) ext2_blocks_a = 1;
-    if (ext2_blocks_b < 1) ext2_blocks_b = 1;
-    IZ_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_blocks, extend_kernel, kThreads, lc.smem));
-    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext4_blocks, extend_g4_kernel, kThreads, lc.smem4));
-    if (ext_blocks < 1) ext_blocks = 1;
-    if (ext4_blocks < 1) ext4_blocks = 1;
+  OccupancyCache& oc = ctx->occ;  // per context: function attributes and occupancy belong to a device
+  if (!oc.ext) {
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.ext2[0], extend_g2_kernel<kG2Stack, false>, kExt2Threads, smem2_a));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.ext2[1], extend_g2_kernel<kG2StackDeep, false>, kExt2Threads, smem2_b));
+    if (oc.ext2[0] < 1) oc.ext2[0] = 1;
+    if (oc.ext2[1] < 1) oc.ext2[1] = 1;
+    IZ_CUDA(cudaFuncSetAttribute(extend_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
+    IZ_CUDA(cudaFuncSetAttribute(extend_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.ext4, extend_g4_kernel<false>, kThreads, lc.smem4));
+    if (oc.ext4 < 1) oc.ext4 = 1;
+    IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.ext, extend_kernel<false>, kThreads, lc.smem));
+    if (oc.ext < 1) oc.ext = 1;
   }
-  lc.ext_blocks = ext_blocks; lc.ext4_blocks = ext4_blocks; lc.ext2_blocks = lc.g2_deep ? ext2_blocks_b : ext2_blocks_a;
+  lc.ext_blocks = oc.ext; lc.ext4_blocks = oc.ext4; lc.ext2_blocks = oc.ext2[lc.g2_deep ? 1 : 0];
   // tiny trees (config 4 has 22 primitives) stay cache-resident and coherent: the thread-per-ray stage wins there
   lc.use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= 64;
   lc.use_g2 = lc.use_g4 && ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2StackDeep;
+  lc.count = ctx->render && ctx->render->count_on;
+  return IZPI_OK;
+}
+
+// IZPI_RENDER_STATS: events around the stages of a bounce
+int span_begin(RenderState* r, cudaStream_t st, int kind) {
+  if (!r->stats_on) return IZPI_OK;
+  while (r->ev_used + 2 > r->ev_pool.size()) {
+    cudaEvent_t e;
+    IZ_CUDA(cudaEventCreate(&e));
+    r->ev_pool.push_back(e);
+  }
+  RenderState::Span sp{r->ev_pool[r->ev_used], r->ev_pool[r->ev_used + 1], kind};
+  r->ev_used += 2;
+  IZ_CUDA(cudaEventRecord(sp.a, st));
+  r->spans.push_back(sp);
+  return IZPI_OK;
+}
+int span_end(RenderState* r, cudaStream_t st) {
+  if (!r->stats_on) return IZPI_OK;
+  IZ_CUDA(cudaEventRecord(r->spans.back().b, st));
   return IZPI_OK;
 }
 
@@ -798,15 +854,24 @@ int batch_start(izpi_ctx* ctx, RenderState* r, BatchSlot& s, int batch, const ui
     s.pixel_capacity = n_pixels;
   }
   IZ_CUDA(cudaMemcpyAsync(s.d_pixels, px, (size_t)n_pixels * 4, cudaMemcpyHostToDevice, st));
-  IZ_CUDA(cudaMemsetAsync(s.q.counters, 0, 9 * sizeof(unsigned long long), st));
+  IZ_CUDA(cudaMemsetAsync(s.q.counters, 0, 11 * sizeof(unsigned long long), st));
   long long n = (long long)n_pixels * s_count;
   int gen_grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
-  int rc = launch(ctx, st, raygen_kernel, dim3(gen_grid), dim3(256), 0, ctx->scene, r->rp, s.d_paths, s.d_pixels, n_pixels, s_begin,
-                  s_count, s.q);
+  int rc = span_begin(r, st, 2);
   if (rc != IZPI_OK) return rc;
+  rc = launch(ctx, st, raygen_kernel, dim3(gen_grid), dim3(256), 0, ctx->scene, r->rp, s.d_paths, s.d_pixels, n_pixels, s_begin,
+              s_count, s.q);
+  if (rc != IZPI_OK) return rc;
+  if ((rc = span_end(r, st)) != IZPI_OK) return rc;
   s.busy = true; s.drained = false; s.batch = batch; s.n_pixels = n_pixels; s.s_begin = s_begin; s.s_count = s_count;
   s.bounce = 0; s.live = (unsigned long long)n;
   return IZPI_OK;
+}
+
+template <int CLS>
+int launch_shade(izpi_ctx* ctx, RenderState* r, BatchSlot& s, int grid) {
+  if (!((ctx->scene.class_mask >> CLS) & 1)) return IZPI_OK;  // no primitive carries this class: its bin stays empty
+  return launch(ctx, s.stream, shade_kernel<CLS>, dim3(grid), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q);
 }
 
 // One bounce of a batch.  The live count of bounce b-2 is harvested first (the host runs at most two bounces ahead
@@ -820,30 +885,36 @@ int batch_step(izpi_ctx* ctx, RenderState* r, BatchSlot& s, const LaunchCfg& lc)
   }
   if (s.live == 0 || s.bounce > r->rp.max_depth || s.bounce >= kMaxBounces) { s.drained = true; return IZPI_OK; }
   int rc;
+  if ((rc = span_begin(r, st, 0)) != IZPI_OK) return rc;
   long long want = ((long long)s.live + kThreads - 1) / kThreads;
   if (lc.use_g2) {
     long long want2 = ((long long)s.live + (kExt2Threads / 2) - 1) / (kExt2Threads / 2);
     int eg2 = (int)std::max<long long>(1, std::min<long long>(want2, (long long)sm * lc.ext2_blocks));
-    if ((rc = launch(ctx, st, lc.g2_deep ? extend_g2_kernel<kG2StackDeep> : extend_g2_kernel<kG2Stack>, dim3(eg2), dim3(kExt2Threads), lc.smem2, ctx->scene, r->rp, s.d_paths, s.q,
-                     ctx->pair_stragglers)) != IZPI_OK) return rc;
+    auto k = lc.g2_deep ? (lc.count ? extend_g2_kernel<kG2StackDeep, true> : extend_g2_kernel<kG2StackDeep, false>)
+                        : (lc.count ? extend_g2_kernel<kG2Stack, true> : extend_g2_kernel<kG2Stack, false>);
+    if ((rc = launch(ctx, st, k, dim3(eg2), dim3(kExt2Threads), lc.smem2, ctx->scene, r->rp, s.d_paths, s.q, ctx->pair_stragglers)) != IZPI_OK) return rc;
   } else if (lc.use_g4) {
     long long want4 = ((long long)s.live + (kThreads / 4) - 1) / (kThreads / 4);
     int eg4 = (int)std::max<long long>(1, std::min<long long>(want4, (long long)sm * lc.ext4_blocks));
-    if ((rc = launch(ctx, st, extend_g4_kernel, dim3(eg4), dim3(kThreads), lc.smem4, ctx->scene, r->rp, s.d_paths, s.q,
-                     ctx->node_stragglers)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, st, lc.count ? extend_g4_kernel<true> : extend_g4_kernel<false>, dim3(eg4), dim3(kThreads), lc.smem4, ctx->scene, r->rp,
+                     s.d_paths, s.q, ctx->node_stragglers)) != IZPI_OK) return rc;
   } else {
     int eg = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * lc.ext_blocks));
-    if ((rc = launch(ctx, st, extend_kernel, dim3(eg), dim3(kThreads), lc.smem, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, st, lc.count ? extend_kernel<true> : extend_kernel<false>, dim3(eg), dim3(kThreads), lc.smem, ctx->scene, r->rp, s.d_paths,
+                     s.q)) != IZPI_OK) return rc;
   }
+  if ((rc = span_end(r, st)) != IZPI_OK) return rc;
+  if ((rc = span_begin(r, st, 1)) != IZPI_OK) return rc;
   int sg = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * 8));
-  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_LAMBERT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
-  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_METAL>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
-  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_DIELECTRIC>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
-  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_DIFFUSE_LIGHT>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
-  if ((rc = launch(ctx, st, shade_kernel<IZPI_MAT_PBR>, dim3(sg), dim3(kThreads), 0, ctx->scene, r->rp, s.d_paths, s.q)) != IZPI_OK) return rc;
+  if ((rc = launch_shade<IZPI_MAT_LAMBERT>(ctx, r, s, sg)) != IZPI_OK) return rc;
+  if ((rc = launch_shade<IZPI_MAT_METAL>(ctx, r, s, sg)) != IZPI_OK) return rc;
+  if ((rc = launch_shade<IZPI_MAT_DIELECTRIC>(ctx, r, s, sg)) != IZPI_OK) return rc;
+  if ((rc = launch_shade<IZPI_MAT_DIFFUSE_LIGHT>(ctx, r, s, sg)) != IZPI_OK) return rc;
+  if ((rc = launch_shade<IZPI_MAT_PBR>(ctx, r, s, sg)) != IZPI_OK) return rc;
   std::swap(s.q.cur, s.q.next);
   Queues qs = s.q;  // after the swap: cur = survivors; advance moves the count
   if ((rc = launch(ctx, st, advance_kernel, dim3(1), dim3(1), 0, qs, s.d_count_mapped + (s.bounce & 7))) != IZPI_OK) return rc;
+  if ((rc = span_end(r, st)) != IZPI_OK) return rc;
   IZ_CUDA(cudaEventRecord(s.ev[s.bounce & 7], st));
   s.bounce++;
   return IZPI_OK;
@@ -853,10 +924,13 @@ int batch_step(izpi_ctx* ctx, RenderState* r, BatchSlot& s, const LaunchCfg& lc)
 int batch_finish(izpi_ctx* ctx, RenderState* r, BatchSlot& s, cudaEvent_t prev_resolved) {
   cudaStream_t st = s.stream;
   if (prev_resolved) IZ_CUDA(cudaStreamWaitEvent(st, prev_resolved, 0));
-  int rc = launch(ctx, st, resolve_kernel, dim3((s.n_pixels + 127) / 128), dim3(128), 0, r->rp, s.d_paths, s.d_pixels, s.n_pixels,
-                  s.s_count, r->d_canvas);
+  int rc = span_begin(r, st, 2);
+  if (rc != IZPI_OK) return rc;
+  rc = launch(ctx, st, resolve_kernel, dim3((s.n_pixels + 127) / 128), dim3(128), 0, r->rp, s.d_paths, s.d_pixels, s.n_pixels,
+              s.s_count, r->d_canvas);
   if (rc != IZPI_OK) return rc;
   if ((rc = launch(ctx, st, accumulate_traced_kernel, dim3(1), dim3(1), 0, s.q.counters, r->d_total_rays)) != IZPI_OK) return rc;
+  if ((rc = span_end(r, st)) != IZPI_OK) return rc;
   IZ_CUDA(cudaEventRecord(s.resolved, st));
   s.busy = false;
   return IZPI_OK;
@@ -867,44 +941,46 @@ int sync_slots(RenderState* r) {
   return IZPI_OK;
 }
 
-int canvas_to_host(izpi_ctx* ctx, RenderState* r, double* host, bool epilogue) {
+// device side of the frame's tail: mean over spp into d_out, then the spectral epilogue (renderer.go:216-219)
+int canvas_epilogue(izpi_ctx* ctx, RenderState* r, bool epilogue) {
   cudaStream_t st = ctx->stream;
   long long n_px = (long long)r->rp.width * r->rp.height;
   int rc;
   if ((rc = sync_slots(r)) != IZPI_OK) return rc;
   if ((rc = launch(ctx, st, mean_kernel, dim3((unsigned)((n_px + 255) / 256)), dim3(256), 0, r->rp, r->d_canvas, r->d_out, n_px)) != IZPI_OK) return rc;
-  if (epilogue && r->rp.sampler == IZPI_SAMPLER_SPECTRAL) {  // renderer.go:216-219
+  if (epilogue && r->rp.sampler == IZPI_SAMPLER_SPECTRAL) {
     IZ_CUDA(cudaMemcpyAsync(r->d_snap, r->d_out, (size_t)n_px * 32, cudaMemcpyDeviceToDevice, st));
     dim3 b(32, 8), g((r->rp.width + 31) / 32, (r->rp.height + 7) / 8);
     if ((rc = launch(ctx, st, firefly_kernel, g, b, 0, r->d_snap, r->d_out, r->rp.width, r->rp.height)) != IZPI_OK) return rc;
     if ((rc = launch(ctx, st, xyz_to_acescg_kernel, dim3((unsigned)((n_px + 255) / 256)), dim3(256), 0, r->d_out, n_px,
                      ctx->scene.camera.exposure)) != IZPI_OK) return rc;
   }
-  IZ_CUDA(cudaMemcpyAsync(host, r->d_out, (size_t)n_px * 32, cudaMemcpyDeviceToHost, st));
-  IZ_CUDA(cudaStreamSynchronize(st));
   return IZPI_OK;
 }
 
-}  // namespace
+int canvas_to_host(izpi_ctx* ctx, RenderState* r, double* host, bool epilogue) {
+  int rc = canvas_epilogue(ctx, r, epilogue);
+  if (rc != IZPI_OK) return rc;
+  long long n_px = (long long)r->rp.width * r->rp.height;
+  IZ_CUDA(cudaMemcpyAsync(host, r->d_out, (size_t)n_px * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  IZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return IZPI_OK;
+}
 
-extern "C" {
+// Rows of the device / host canvas that hold the pixels of a run of tiles: image row y lives at canvas row H - y
+// (rgb.go:41); y == 0 falls into the hidden row H, which never leaves the device on this path.
+bool run_rows(const RenderState* r, const TileRun& t, int& row0, int& rows) {
+  const int H = r->rp.height;
+  int lo = H - (int)t.y1, hi = H - (int)t.y0;  // inclusive canvas rows
+  if (hi > H - 1) hi = H - 1;
+  if (lo < 0) lo = 0;
+  row0 = lo; rows = hi - lo + 1;
+  return rows > 0;
+}
 
-int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
-  if (!ctx || !cfg) { set_error("izpi_render_setup: bad argument"); return IZPI_EINVAL; }
-  if (!ctx->has_scene) { set_error("izpi_render_setup: no scene uploaded"); return IZPI_ESTATE; }
-  if (cfg->width <= 0 || cfg->height <= 0 || cfg->width > 65535 || cfg->height > 65535 || cfg->spp <= 0 || cfg->max_depth < 0 ||
-      cfg->sample_count < 0 || cfg->sample_offset < 0 || cfg->sample_offset + cfg->sample_count > cfg->spp ||
-      cfg->sampler < IZPI_SAMPLER_COLOUR || cfg->sampler > IZPI_SAMPLER_NORMAL) {
-    set_error("izpi_render_setup: invalid configuration");
-    return IZPI_EINVAL;
-  }
-  if (ctx->scene.n_lights == 0 && cfg->sampler <= IZPI_SAMPLER_SPECTRAL) {  // HitableSlice.Random indexes an empty slice: the reference panics
-    set_error("izpi_render_setup: scene has no emitters (scene.Lights is empty)");
-    return IZPI_EINVAL;
-  }
-  if (!ctx->scene.attrs) { set_error("izpi_render_setup: scene was uploaded without tri_attrs"); return IZPI_ESTATE; }
+int setup_one(izpi_ctx* ctx, const izpi_render_config* cfg) {
   IZ_CUDA(cudaSetDevice(ctx->device));
-  int rc = upload_cie();
+  int rc = upload_cie(ctx);
   if (rc != IZPI_OK) return rc;
   // the big buffers (path states, queues, canvas) are allocated once per context and reused by later
   // setups: a render call then costs no cudaMalloc / cudaFree
@@ -916,6 +992,11 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
     if (e) { long v = atol(e); if (v >= 1024 && v <= (1l << 28)) r->batch_paths = (int32_t)v; }
   }
   r->cfg = *cfg;
+  r->stats_on = (cfg->flags & (IZPI_RENDER_STATS | IZPI_RENDER_TIMING)) != 0;
+  r->count_on = (cfg->flags & IZPI_RENDER_STATS) != 0;
+  r->spans.clear(); r->ev_used = 0;
+  std::memset(&r->stats, 0, sizeof(r->stats));
+  r->rendered.clear(); r->rendered_pixels = 0;
   RenderParams& rp = r->rp;
   rp.width = cfg->width; rp.height = cfg->height; rp.spp = cfg->spp; rp.max_depth = cfg->max_depth; rp.sampler = cfg->sampler;
   for (int k = 0; k < 3; k++) rp.background[k] = cfg->background[k];
@@ -938,7 +1019,7 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
     r->canvas_capacity = n_px_hidden;
   }
   if (!r->allocated) {
-    IZ_CUDA(cudaMalloc(&r->d_total_rays, sizeof(unsigned long long)));
+    IZ_CUDA(cudaMalloc(&r->d_total_rays, 4 * sizeof(unsigned long long)));
     int32_t cap = r->batch_paths;
     for (BatchSlot& s : r->slot) {
       IZ_CUDA(cudaMalloc(&s.d_paths, (size_t)cap * sizeof(PathState)));
@@ -958,72 +1039,163 @@ int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
   rc = sync_slots(r);
   if (rc != IZPI_OK) return rc;
   IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px_hidden * 32, ctx->stream));
-  IZ_CUDA(cudaMemsetAsync(r->d_total_rays, 0, sizeof(unsigned long long), ctx->stream));
+  IZ_CUDA(cudaMemsetAsync(r->d_total_rays, 0, 4 * sizeof(unsigned long long), ctx->stream));
   IZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return IZPI_OK;
 }
 
-int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* tiles, double* canvas_rgba) {
-  if (!ctx || n_tiles < 0 || (n_tiles > 0 && !tiles)) { set_error("izpi_render_tiles: bad argument"); return IZPI_EINVAL; }
+// The render loop of ONE device over a tile list whose cursor may be shared with other contexts.
+int tiles_one(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* tiles, uint64_t* cursor, int sharers) {
   RenderState* r = ctx->render;
-  if (!r) { set_error("izpi_render_tiles: izpi_render_setup has not been called"); return IZPI_ESTATE; }
   IZ_CUDA(cudaSetDevice(ctx->device));
-  // pixel list in the reference's loop order: tiles as given, rows y0..y1, columns x0..x1 (rgb.go:27-29)
-  std::vector<uint32_t> px;
-  for (int32_t t = 0; t < n_tiles; t++) {
-    uint32_t x0 = tiles[4 * t], y0 = tiles[4 * t + 1], x1 = tiles[4 * t + 2], y1 = tiles[4 * t + 3];
-    if (x1 < x0 || y1 < y0 || x1 >= (uint32_t)r->rp.width || y1 >= (uint32_t)r->rp.height) {
-      set_error("izpi_render_tiles: tile outside the image");
-      return IZPI_EINVAL;
-    }
-    for (uint32_t y = y0; y <= y1; y++)
-      for (uint32_t x = x0; x <= x1; x++) px.push_back(x | (y << 16));
-  }
   const int s_total = r->cfg.sample_count, s_off = r->cfg.sample_offset;
-  if (!px.empty() && s_total > 0) {
+  if (n_tiles == 0 || s_total <= 0) return IZPI_OK;
+  uint64_t private_cursor = 0;
+  if (!cursor) { cursor = &private_cursor; sharers = 1; }
+  if (sharers < 1) sharers = 1;
+  const int64_t cap = r->slot[0].q.capacity;
+  struct Batch { std::vector<uint32_t>* px; int64_t p0; int np, s0, sc; };
+  std::deque<std::vector<uint32_t>> claims;  // pixel lists stay alive until the frame is done
+  std::deque<Batch> pending;
+  bool exhausted = false;
+  // Claim the next run of tiles (izpi_host_claim_tiles): everything at once for a private cursor (then split as before),
+  // otherwise guided self-scheduling.
+  auto claim = [&]() {
+    const long long tile_paths = (long long)(tiles[2] - tiles[0] + 1) * (tiles[3] - tiles[1] + 1) * s_total;
+    int32_t t0 = 0, t1 = 0;
+    if (!izpi_host_claim_tiles(cursor, n_tiles, tile_paths, cap, sharers == 1 ? 1 : sharers * kSlots, &t0, &t1)) { exhausted = true; return; }
+    // pixel list in the reference's loop order: tiles as given, rows y0..y1, columns x0..x1 (rgb.go:27-29)
+    claims.emplace_back();
+    std::vector<uint32_t>& px = claims.back();
+    for (int t = t0; t < t1; t++) {
+      const uint32_t x0 = tiles[4 * t], y0 = tiles[4 * t + 1], x1 = tiles[4 * t + 2], y1 = tiles[4 * t + 3];
+      for (uint32_t y = y0; y <= y1; y++)
+        for (uint32_t x = x0; x <= x1; x++) px.push_back(x | (y << 16));
+      if (!r->rendered.empty() && r->rendered.back().y0 == y0 && r->rendered.back().y1 == y1 && r->rendered.back().x1 + 1 == x0) r->rendered.back().x1 = x1;
+      else r->rendered.push_back({x0, y0, x1, y1});
+      r->rendered_pixels += (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
+    }
     // batches: as many samples per pixel as fit, then as many pixels as fit; sample blocks in
     // increasing order so that every pixel's running sum adds its samples in the reference's order
-    struct Batch { int64_t p0; int np, s0, sc; };
-    std::vector<Batch> batches;
-    const int64_t cap = r->slot[0].q.capacity;
     int s_block = (int)std::min<int64_t>(s_total, cap);
     int64_t px_block = std::max<int64_t>(1, cap / s_block);
     // keep both slots busy even when everything would fit one batch
-    if ((int64_t)px.size() <= px_block && s_block == s_total && (int64_t)px.size() * s_total > (1 << 20))
+    if (sharers == 1 && (int64_t)px.size() <= px_block && s_block == s_total && (int64_t)px.size() * s_total > (1 << 20))
       px_block = ((int64_t)px.size() + 1) / 2;
     for (int64_t p0 = 0; p0 < (int64_t)px.size(); p0 += px_block) {
       int np = (int)std::min<int64_t>(px_block, (int64_t)px.size() - p0);
-      for (int s0 = 0; s0 < s_total; s0 += s_block) batches.push_back({p0, np, s_off + s0, std::min(s_block, s_total - s0)});
+      for (int s0 = 0; s0 < s_total; s0 += s_block) pending.push_back({&px, p0, np, s_off + s0, std::min(s_block, s_total - s0)});
     }
-    LaunchCfg lc;
-    int rc = launch_cfg(ctx, lc);
-    if (rc != IZPI_OK) return rc;
-    size_t next = 0;
-    int resolved_upto = 0;          // batches [0, resolved_upto) have their resolve enqueued
-    cudaEvent_t last_resolved = nullptr;
-    for (;;) {
-      bool any = false;
-      for (BatchSlot& s : r->slot) {
-        if (!s.busy && next < batches.size()) {
-          const Batch& b = batches[next];
-          if ((rc = batch_start(ctx, r, s, (int)next, px.data() + b.p0, b.np, b.s0, b.sc)) != IZPI_OK) return rc;
-          next++;
-        }
-        if (!s.busy) continue;
-        any = true;
-        if (!s.drained && (rc = batch_step(ctx, r, s, lc)) != IZPI_OK) return rc;
-        if (s.drained && s.batch == resolved_upto) {  // resolves strictly in batch order
-          if ((rc = batch_finish(ctx, r, s, last_resolved)) != IZPI_OK) return rc;
-          last_resolved = s.resolved;
-          resolved_upto++;
+  };
+  LaunchCfg lc;
+  int rc = launch_cfg(ctx, lc);
+  if (rc != IZPI_OK) return rc;
+  int started = 0, resolved_upto = 0;  // batches [0, resolved_upto) have their resolve enqueued
+  cudaEvent_t last_resolved = nullptr;
+  for (;;) {
+    bool any = false;
+    for (BatchSlot& s : r->slot) {
+      if (r->stats_on && &s != &r->slot[0]) continue;  // stage times are meaningful only without overlap
+      if (!s.busy) {
+        if (pending.empty() && !exhausted) claim();
+        if (!pending.empty()) {
+          const Batch b = pending.front();
+          pending.pop_front();
+          if ((rc = batch_start(ctx, r, s, started, b.px->data() + b.p0, b.np, b.s0, b.sc)) != IZPI_OK) return rc;
+          started++;
         }
       }
-      if (!any && next >= batches.size()) break;
+      if (!s.busy) continue;
+      any = true;
+      if (!s.drained && (rc = batch_step(ctx, r, s, lc)) != IZPI_OK) return rc;
+      if (s.drained && s.batch == resolved_upto) {  // resolves strictly in batch order
+        if ((rc = batch_finish(ctx, r, s, last_resolved)) != IZPI_OK) return rc;
+        last_resolved = s.resolved;
+        resolved_upto++;
+      }
     }
-    if ((rc = sync_slots(r)) != IZPI_OK) return rc;
+    if (!any && pending.empty() && exhausted) break;
   }
-  if (canvas_rgba) return canvas_to_host(ctx, r, canvas_rgba, false);
+  if ((rc = sync_slots(r)) != IZPI_OK) return rc;
+  if (r->stats_on) {
+    for (const RenderState::Span& sp : r->spans) {
+      float ms = 0;
+      IZ_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+      if (sp.kind == 0) { r->stats.extend_ms += ms; r->stats.extend_launches++; }
+      else if (sp.kind == 1) r->stats.shade_ms += ms;
+      else r->stats.other_ms += ms;
+    }
+    r->spans.clear(); r->ev_used = 0;
+  }
   return IZPI_OK;
+}
+
+int check_tiles(const RenderState* r, int32_t n_tiles, const uint32_t* tiles, const char* who) {
+  for (int32_t t = 0; t < n_tiles; t++) {
+    uint32_t x0 = tiles[4 * t], y0 = tiles[4 * t + 1], x1 = tiles[4 * t + 2], y1 = tiles[4 * t + 3];
+    if (x1 < x0 || y1 < y0 || x1 >= (uint32_t)r->rp.width || y1 >= (uint32_t)r->rp.height) {
+      set_error(std::string(who) + ": tile outside the image");
+      return IZPI_EINVAL;
+    }
+  }
+  return IZPI_OK;
+}
+
+int read_totals(izpi_ctx* ctx, unsigned long long v[3]) {
+  RenderState* r = ctx->render;
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  int rc = sync_slots(r);
+  if (rc != IZPI_OK) return rc;
+  IZ_CUDA(cudaMemcpy(v, r->d_total_rays, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return IZPI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int izpi_render_setup(izpi_ctx* ctx, const izpi_render_config* cfg) {
+  if (!ctx || !cfg) { set_error("izpi_render_setup: bad argument"); return IZPI_EINVAL; }
+  if (!ctx->has_scene) { set_error("izpi_render_setup: no scene uploaded"); return IZPI_ESTATE; }
+  if (cfg->width <= 0 || cfg->height <= 0 || cfg->width > 65535 || cfg->height > 65535 || cfg->spp <= 0 || cfg->max_depth < 0 ||
+      cfg->sample_count < 0 || cfg->sample_offset < 0 || cfg->sample_offset + cfg->sample_count > cfg->spp ||
+      cfg->sampler < IZPI_SAMPLER_COLOUR || cfg->sampler > IZPI_SAMPLER_NORMAL) {
+    set_error("izpi_render_setup: invalid configuration");
+    return IZPI_EINVAL;
+  }
+  if (ctx->scene.n_lights == 0 && cfg->sampler <= IZPI_SAMPLER_SPECTRAL) {  // HitableSlice.Random indexes an empty slice: the reference panics
+    set_error("izpi_render_setup: scene has no emitters (scene.Lights is empty)");
+    return IZPI_EINVAL;
+  }
+  if (!ctx->scene.attrs && ctx->scene.n_prims > 0) { set_error("izpi_render_setup: scene was uploaded without tri_attrs"); return IZPI_ESTATE; }
+  return group_run(ctx, [&](izpi_ctx* m, int) { return setup_one(m, cfg); });
+}
+
+int izpi_render_tiles_shared(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* tiles, uint64_t* cursor, int32_t sharers, double* canvas_rgba) {
+  if (!ctx || n_tiles < 0 || (n_tiles > 0 && !tiles)) { set_error("izpi_render_tiles: bad argument"); return IZPI_EINVAL; }
+  RenderState* r = ctx->render;
+  if (!r) { set_error("izpi_render_tiles: izpi_render_setup has not been called"); return IZPI_ESTATE; }
+  int rc = check_tiles(r, n_tiles, tiles, "izpi_render_tiles");
+  if (rc != IZPI_OK) return rc;
+  if (ctx->subs.empty()) {
+    if ((rc = tiles_one(ctx, n_tiles, tiles, cursor, sharers)) != IZPI_OK) return rc;
+  } else {
+    // device group: one host thread per GPU, all claiming from one cursor (the caller's, when it shares the list further)
+    const int members = 1 + (int)ctx->subs.size();
+    ctx->group_cursor = 0;
+    uint64_t* cur = cursor ? cursor : &ctx->group_cursor;
+    const int all = cursor ? (sharers < 1 ? 1 : sharers) * members : members;
+    if ((rc = group_run(ctx, [&](izpi_ctx* m, int) { return tiles_one(m, n_tiles, tiles, cur, all); })) != IZPI_OK) return rc;
+  }
+  if (canvas_rgba) {
+    if (!ctx->subs.empty()) { set_error("izpi_render_tiles: a device group delivers the canvas through izpi_render_finish"); return IZPI_EINVAL; }
+    return canvas_to_host(ctx, r, canvas_rgba, false);
+  }
+  return IZPI_OK;
+}
+
+int izpi_render_tiles(izpi_ctx* ctx, int32_t n_tiles, const uint32_t* tiles, double* canvas_rgba) {
+  return izpi_render_tiles_shared(ctx, n_tiles, tiles, nullptr, 1, canvas_rgba);
 }
 
 int izpi_render_tile_rows(izpi_ctx* ctx, uint32_t strip_height, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, double* rows) {
@@ -1032,8 +1204,9 @@ int izpi_render_tile_rows(izpi_ctx* ctx, uint32_t strip_height, uint32_t x0, uin
   if (!r) { set_error("izpi_render_tile_rows: izpi_render_setup has not been called"); return IZPI_ESTATE; }
   if (strip_height == 0) { set_error("izpi_render_tile_rows: strip_height 0 (the reference indexes an empty slice here)"); return IZPI_EINVAL; }
   const uint32_t tile[4] = {x0, y0, x1, y1};
-  int rc = izpi_render_tiles(ctx, 1, tile, nullptr);  // validates the bounds
+  int rc = check_tiles(r, 1, tile, "izpi_render_tile_rows");
   if (rc != IZPI_OK) return rc;
+  if ((rc = tiles_one(ctx, 1, tile, nullptr, 1)) != IZPI_OK) return rc;  // a worker is one device: the group's first
   const int w = (int)(x1 - x0 + 1), h = (int)(y1 - y0 + 1);
   const long long stride = (long long)strip_height * 4 * w;
   double* d_rows = nullptr;
@@ -1055,10 +1228,31 @@ int izpi_render_tile_rows(izpi_ctx* ctx, uint32_t strip_height, uint32_t x0, uin
 int izpi_render_canvas_device(izpi_ctx* ctx, double** d_canvas) {
   if (!ctx || !d_canvas) { set_error("izpi_render_canvas_device: bad argument"); return IZPI_EINVAL; }
   if (!ctx->render) { set_error("izpi_render_canvas_device: izpi_render_setup has not been called"); return IZPI_ESTATE; }
+  IZ_CUDA(cudaSetDevice(ctx->device));
   int rc = sync_slots(ctx->render);
   if (rc != IZPI_OK) return rc;
   IZ_CUDA(cudaStreamSynchronize(ctx->stream));
   *d_canvas = ctx->render->d_canvas;
+  return IZPI_OK;
+}
+
+int izpi_render_get_stats(izpi_ctx* ctx, izpi_render_stats* out) {
+  if (!ctx || !out) { set_error("izpi_render_get_stats: bad argument"); return IZPI_EINVAL; }
+  if (!ctx->render) { set_error("izpi_render_get_stats: izpi_render_setup has not been called"); return IZPI_ESTATE; }
+  std::memset(out, 0, sizeof(*out));
+  std::vector<izpi_ctx*> members{ctx};
+  members.insert(members.end(), ctx->subs.begin(), ctx->subs.end());
+  for (izpi_ctx* m : members) {
+    unsigned long long v[3];
+    int rc = read_totals(m, v);
+    if (rc != IZPI_OK) return rc;
+    const izpi_render_stats& s = m->render->stats;
+    out->rays += v[0]; out->nodes_visited += v[1]; out->prim_tests += v[2];
+    out->extend_launches += s.extend_launches;
+    out->extend_ms = std::max(out->extend_ms, s.extend_ms); out->shade_ms = std::max(out->shade_ms, s.shade_ms);
+    out->other_ms = std::max(out->other_ms, s.other_ms);  // members run concurrently
+  }
+  cudaSetDevice(ctx->device);
   return IZPI_OK;
 }
 
@@ -1068,14 +1262,73 @@ int izpi_render_finish(izpi_ctx* ctx, double* canvas_rgba, uint64_t* total_rays)
   if (!r) { set_error("izpi_render_finish: izpi_render_setup has not been called"); return IZPI_ESTATE; }
   IZ_CUDA(cudaSetDevice(ctx->device));
   if (total_rays) {
-    int rc = sync_slots(r);
+    izpi_render_stats st;
+    int rc = izpi_render_get_stats(ctx, &st);
     if (rc != IZPI_OK) return rc;
-    unsigned long long v = 0;
-    IZ_CUDA(cudaMemcpy(&v, r->d_total_rays, sizeof(v), cudaMemcpyDeviceToHost));
-    *total_rays = v;
+    *total_rays = st.rays;
   }
-  if (canvas_rgba) return canvas_to_host(ctx, r, canvas_rgba, true);
-  return IZPI_OK;
+  if (!canvas_rgba) return IZPI_OK;
+  if (ctx->subs.empty()) return canvas_to_host(ctx, r, canvas_rgba, true);
+
+  // ---- device group: pixels are disjoint, so every member moves only what it rendered ----
+  const int W = r->rp.width, H = r->rp.height;
+  const size_t pitch = (size_t)W * 32;
+  if (r->rp.sampler == IZPI_SAMPLER_SPECTRAL) {
+    // FireflyRejection reads 3x3 neighbourhoods across tile edges (firefly_rejection.go:40-73): the sums of the other
+    // members' tiles go to the first device (peer copies of the rendered runs only), which runs the epilogue on the frame
+    int rc = group_run(ctx, [&](izpi_ctx* m, int i) -> int {
+      if (i == 0) return sync_slots(m->render);
+      RenderState* mr = m->render;
+      int rc2 = sync_slots(mr);
+      if (rc2 != IZPI_OK) return rc2;
+      for (const TileRun& t : mr->rendered) {
+        int row0, rows;
+        if (!run_rows(mr, t, row0, rows)) continue;
+        const size_t off = ((size_t)row0 * W + t.x0) * 4;
+        IZ_CUDA(cudaMemcpy2DAsync(r->d_canvas + off, pitch, mr->d_canvas + off, pitch, (size_t)(t.x1 - t.x0 + 1) * 32, (size_t)rows,
+                                  cudaMemcpyDefault, m->stream));
+      }
+      IZ_CUDA(cudaStreamSynchronize(m->stream));
+      return IZPI_OK;
+    });
+    if (rc != IZPI_OK) return rc;
+    return canvas_to_host(ctx, r, canvas_rgba, true);
+  }
+  // RGB / AOV samplers: each member takes the mean of its own canvas and writes its runs straight into the caller's
+  // canvas -- N device-to-host streams in parallel, nothing crosses the first device.  Pixels nobody rendered are zero,
+  // as in the reference's fresh Float64NRGBA (row 0 always is: rgb.go:41 never writes it).
+  long long covered = 0;
+  for (const izpi_ctx* m : ctx->subs) covered += m->render->rendered_pixels;
+  covered += r->rendered_pixels;
+  const bool full = covered == (long long)W * H;  // the tile grid of the whole image: only canvas row 0 is left over
+  const int members = 1 + (int)ctx->subs.size();
+  auto copy_runs = [&](izpi_ctx* m) -> int {
+    RenderState* mr = m->render;
+    for (const TileRun& t : mr->rendered) {
+      int row0, rows;
+      if (!run_rows(mr, t, row0, rows)) continue;
+      const size_t off = ((size_t)row0 * W + t.x0) * 4;
+      IZ_CUDA(cudaMemcpy2DAsync(canvas_rgba + off, pitch, mr->d_out + off, pitch, (size_t)(t.x1 - t.x0 + 1) * 32, (size_t)rows,
+                                cudaMemcpyDeviceToHost, m->stream));
+    }
+    IZ_CUDA(cudaStreamSynchronize(m->stream));
+    return IZPI_OK;
+  };
+  int rc = group_run(ctx, [&](izpi_ctx* m, int i) -> int {
+    int rc2 = canvas_epilogue(m, m->render, false);
+    if (rc2 != IZPI_OK) return rc2;
+    IZ_CUDA(cudaStreamSynchronize(m->stream));
+    if (full) {
+      if (i == 0) std::memset(canvas_rgba, 0, pitch);
+      return copy_runs(m);
+    }
+    // partial frame: every member clears a share of the caller's canvas; the runs follow once all shares are clear
+    const size_t total = (size_t)H * pitch, b0 = total / members * i, b1 = i == members - 1 ? total : total / members * (i + 1);
+    std::memset(reinterpret_cast<char*>(canvas_rgba) + b0, 0, b1 - b0);
+    return IZPI_OK;
+  });
+  if (rc == IZPI_OK && !full) rc = group_run(ctx, [&](izpi_ctx* m, int) -> int { return copy_runs(m); });
+  return rc;
 }
 
 }  // extern "C"

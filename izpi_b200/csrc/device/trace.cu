@@ -243,7 +243,7 @@ int launch_g2(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_dir
               double* d_t, cudaStream_t st, bool count, unsigned long long* counters) {
   const size_t smem = (size_t)(kG2Threads / 2) * G2Slab<STACK>::kSlots * sizeof(int2);
   auto k = mode == IZPI_TRACE_FP32 ? trace_g2_kernel<false, true, STACK> : (count ? trace_g2_kernel<true, false, STACK> : trace_g2_kernel<false, false, STACK>);
-  static thread_local int bps = 0;
+  int& bps = ctx->occ.trace_g2[STACK == kG2Stack ? 0 : 1];  // per context: function attributes and occupancy belong to a device
   if (!bps) {
     IZ_CUDA(cudaFuncSetAttribute(trace_g2_kernel<false, false, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IZ_CUDA(cudaFuncSetAttribute(trace_g2_kernel<true, false, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -316,7 +316,7 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
   if (ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && (!ctx->force_scalar || mode == IZPI_TRACE_FP32)) {
     size_t smem4 = (size_t)(kTraceThreads / 4) * kG4Slab * sizeof(int2);
     auto k4 = mode == IZPI_TRACE_FP32 ? trace_g4_kernel<false, true> : (count ? trace_g4_kernel<true, false> : trace_g4_kernel<false, false>);
-    static thread_local int bps4 = 0;
+    int& bps4 = ctx->occ.trace_g4;
     if (!bps4) {
       IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps4, trace_g4_kernel<false, false>, kTraceThreads, smem4));
       if (bps4 < 1) bps4 = 1;
@@ -335,7 +335,7 @@ int launch_trace(izpi_ctx* ctx, int64_t n, const double* d_org, const double* d_
   }
   size_t smem = (size_t)kStackDepth * kTraceThreads * sizeof(int32_t);
   auto kern = count ? trace_kernel<true> : trace_kernel<false>;
-  static thread_local int blocks_per_sm = 0;
+  int& blocks_per_sm = ctx->occ.trace_scalar;
   if (!blocks_per_sm) {
     IZ_CUDA(cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IZ_CUDA(cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -367,10 +367,35 @@ int izpi_trace_closest_device(izpi_ctx* ctx, int64_t n, const double* d_org, con
                       ctx->d_counters);
 }
 
+static int trace_closest_one(izpi_ctx* ctx, int64_t n, const double* org, const double* dir, double tmin, double tmax, int mode,
+                             int32_t* prim_id, double* t, izpi_trace_stats* stats);
+
 int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double* dir, double tmin, double tmax, int mode,
                        int32_t* prim_id, double* t, izpi_trace_stats* stats) {
   if (!ctx || n < 0 || (n > 0 && (!org || !dir || !prim_id || !t))) { set_error("izpi_trace_closest: bad argument"); return IZPI_EINVAL; }
   if (!ctx->has_scene) { set_error("izpi_trace_closest: no scene uploaded"); return IZPI_ESTATE; }
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return IZPI_OK;
+  const int members = 1 + (int)ctx->subs.size();
+  if (members == 1 || n < 2 * members) return trace_closest_one(ctx, n, org, dir, tmin, tmax, mode, prim_id, t, stats);
+  // Device group: rays are independent, so the batch is cut into contiguous slices, one per member; every member runs the
+  // single-device pipeline on its slice and the answers land in disjoint ranges of the caller's buffers (no exchange step).
+  std::vector<izpi_trace_stats> st((size_t)members);
+  int rc = group_run(ctx, [&](izpi_ctx* m, int i) -> int {
+    const int64_t b = n * i / members, e = n * (i + 1) / members;
+    return trace_closest_one(m, e - b, org + 3 * b, dir + 3 * b, tmin, tmax, mode, prim_id + b, t + b, stats ? &st[(size_t)i] : nullptr);
+  });
+  if (rc == IZPI_OK && stats) {
+    for (const izpi_trace_stats& x : st) {
+      stats->rays += x.rays; stats->nodes_visited += x.nodes_visited; stats->prim_tests += x.prim_tests;
+      if (x.kernel_ms > stats->kernel_ms) stats->kernel_ms = x.kernel_ms;  // members run concurrently
+    }
+  }
+  return rc;
+}
+
+static int trace_closest_one(izpi_ctx* ctx, int64_t n, const double* org, const double* dir, double tmin, double tmax, int mode,
+                             int32_t* prim_id, double* t, izpi_trace_stats* stats) {
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return IZPI_OK;
   IZ_CUDA(cudaSetDevice(ctx->device));
@@ -429,7 +454,12 @@ int izpi_trace_closest(izpi_ctx* ctx, int64_t n, const double* org, const double
   return IZPI_OK;
 }
 
-uint64_t izpi_launch_count(const izpi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t izpi_launch_count(const izpi_ctx* ctx) {
+  if (!ctx) return 0;
+  uint64_t v = ctx->launches;
+  for (const izpi_ctx* s : ctx->subs) v += s->launches;
+  return v;
+}
 
 int izpi_debug_ray_aabb4(izpi_ctx* ctx, int32_t n, const float* org, const float* inv, const float* bounds, const float* tmax,
                          uint8_t* masks) {

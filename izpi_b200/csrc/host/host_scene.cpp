@@ -284,6 +284,31 @@ void izpi_host_tiles(int32_t sx, int32_t sy, int32_t* step_x, int32_t* step_y) {
   if (step_y) *step_y = ay;
 }
 
+int izpi_host_claim_tiles(uint64_t* cursor, int32_t n_tiles, int64_t tile_paths, int64_t batch_paths, int32_t takers,
+                          int32_t* begin, int32_t* end) {
+  if (!cursor || !begin || !end || n_tiles <= 0) return 0;
+  if (tile_paths < 1) tile_paths = 1;
+  int64_t grab;
+  if (takers <= 1) {
+    grab = n_tiles;
+  } else {
+    const uint64_t seen = __atomic_load_n(cursor, __ATOMIC_RELAXED);  // a stale value only changes the size of the claim
+    const int64_t left = seen < (uint64_t)n_tiles ? (int64_t)n_tiles - (int64_t)seen : 0;
+    int64_t cap_tiles = batch_paths / tile_paths;
+    if (cap_tiles < 1) cap_tiles = 1;
+    int64_t min_tiles = (((int64_t)1 << 20) + tile_paths - 1) / tile_paths;
+    if (min_tiles > cap_tiles) min_tiles = cap_tiles;
+    grab = left / (2 * (int64_t)takers);
+    if (grab > cap_tiles) grab = cap_tiles;
+    if (grab < min_tiles) grab = min_tiles;
+  }
+  const uint64_t b = __atomic_fetch_add(cursor, (uint64_t)grab, __ATOMIC_RELAXED);
+  if (b >= (uint64_t)n_tiles) return 0;
+  *begin = (int32_t)b;
+  *end = (int32_t)(b + (uint64_t)grab < (uint64_t)n_tiles ? b + (uint64_t)grab : (uint64_t)n_tiles);
+  return 1;
+}
+
 int izpi_host_render(izpi_ctx* ctx, const izpi_render_config* cfg, int32_t tile_begin, int32_t tile_end, int32_t finish,
                      double* canvas, uint64_t* total_rays) {
   if (!ctx || !cfg) { set_error("izpi_host_render: bad argument"); return IZPI_EINVAL; }

@@ -33,19 +33,28 @@ class TraceStats(C.Structure):
 
 class RenderConfig(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
-                ("sampler", C.c_int32), ("sample_offset", C.c_int32), ("sample_count", C.c_int32), ("reserved", C.c_int32),
+                ("sampler", C.c_int32), ("sample_offset", C.c_int32), ("sample_count", C.c_int32), ("flags", C.c_int32),
                 ("background", C.c_double * 3), ("bg_wavelengths", C.c_void_p), ("bg_values", C.c_void_p),
                 ("n_bg", C.c_int32), ("reserved2", C.c_int32), ("seed", C.c_uint64)]
 
 
+class RenderStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("extend_launches", C.c_uint64),
+                ("extend_ms", C.c_double), ("shade_ms", C.c_double), ("other_ms", C.c_double)]
+
+
+RENDER_STATS, RENDER_TIMING = 1, 2
+
 # every symbol include/izpi_cuda.h and include/izpi_host.h declare (checked by tests/test_abi.py)
 EXPORTS = [
-    "izpi_last_error", "izpi_version", "izpi_ctx_create", "izpi_ctx_destroy", "izpi_scene_upload",
+    "izpi_last_error", "izpi_version", "izpi_ctx_create", "izpi_ctx_num_devices", "izpi_ctx_destroy", "izpi_scene_upload",
+    "izpi_scene_image_size", "izpi_scene_image_export", "izpi_scene_image_adopt", "izpi_scene_image_commit",
+    "izpi_render_tiles_shared", "izpi_render_get_stats",
     "izpi_trace_closest", "izpi_trace_closest_device", "izpi_launch_count", "izpi_render_setup", "izpi_render_tiles", "izpi_render_tile_rows",
     "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_debug_fma_peak", "izpi_displace", "izpi_displace_fetch", "izpi_bvh4_build", "izpi_bvh4_build_fetch",
     "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
     "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
-    "izpi_host_tiles", "izpi_host_render",
+    "izpi_host_tiles", "izpi_host_render", "izpi_host_claim_tiles",
     # include/izpi_proto.h
     "izpi_proto_scene_parse", "izpi_proto_scene_append_triangles", "izpi_proto_scene_to_scene", "izpi_proto_scene_spec",
     "izpi_proto_scene_name", "izpi_proto_scene_colour_representation", "izpi_proto_scene_total_triangles",
@@ -85,6 +94,13 @@ def lib():
     L.izpi_bvh4_build_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.izpi_render_setup.argtypes = [C.c_void_p, C.POINTER(RenderConfig)]
     L.izpi_render_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.izpi_render_tiles_shared.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.izpi_render_get_stats.argtypes = [C.c_void_p, C.POINTER(RenderStats)]
+    L.izpi_ctx_num_devices.argtypes = [C.c_void_p]
+    L.izpi_scene_image_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+    L.izpi_scene_image_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.izpi_scene_image_adopt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.izpi_scene_image_commit.argtypes = [C.c_void_p]
     L.izpi_render_tile_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     L.izpi_render_canvas_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.izpi_render_finish.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
@@ -101,6 +117,7 @@ def lib():
     L.izpi_host_scene_upload.argtypes = [C.c_void_p, C.c_void_p]
     L.izpi_host_tiles.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.izpi_host_tiles.restype = None
+    L.izpi_host_claim_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.izpi_host_render.argtypes = [C.c_void_p, C.POINTER(RenderConfig), C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.POINTER(C.c_uint64)]
     _lib = L
@@ -153,14 +170,16 @@ class HostScene:
 
 
 class Context:
-    """One GPU (izpi_ctx)."""
+    """One GPU, or a group of GPUs driven from this process (izpi_ctx; `device` may be an int or a list of ints)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        devs = [int(device)] if isinstance(device, (int, np.integer)) else [int(d) for d in device]
         h = C.c_void_p()
-        ids = (C.c_int * 1)(device)
-        check(lib().izpi_ctx_create(1, ids, C.byref(h)))
+        ids = (C.c_int * len(devs))(*devs)
+        check(lib().izpi_ctx_create(len(devs), ids, C.byref(h)))
         self._h = h
-        self.device = device
+        self.device = devs[0]
+        self.devices = devs
         self._scene = None
 
     def close(self):
@@ -173,6 +192,28 @@ class Context:
     def upload(self, scene: HostScene):
         check(lib().izpi_host_scene_upload(scene._h, self._h))
         self._scene = scene
+
+    # ---- scene image: replicate an uploaded scene onto another device without rebuilding it ----------------------
+    def scene_image(self):
+        """(header bytes, [block sizes], [device pointers]) of the uploaded scene."""
+        hb, nb = C.c_uint64(), C.c_int32()
+        check(lib().izpi_scene_image_size(self._h, C.byref(hb), C.byref(nb)))
+        header = np.zeros(hb.value, dtype=np.uint8)
+        sizes = (C.c_uint64 * max(1, nb.value))()
+        ptrs = (C.c_void_p * max(1, nb.value))()
+        check(lib().izpi_scene_image_export(self._h, header.ctypes.data, sizes, ptrs))
+        return header, [int(sizes[i]) for i in range(nb.value)], [int(ptrs[i] or 0) for i in range(nb.value)]
+
+    def scene_adopt(self, header: np.ndarray, n_blocks: int):
+        """Allocate the blocks of somebody else's scene image here; returns their device pointers (to be filled)."""
+        header = np.ascontiguousarray(header, dtype=np.uint8)
+        ptrs = (C.c_void_p * max(1, n_blocks))()
+        check(lib().izpi_scene_image_adopt(self._h, header.ctypes.data, header.nbytes, ptrs))
+        return [int(ptrs[i] or 0) for i in range(n_blocks)]
+
+    def scene_commit(self):
+        check(lib().izpi_scene_image_commit(self._h))
+        self._scene = None
 
     @property
     def launches(self) -> int:
@@ -271,6 +312,11 @@ class Context:
         rows = np.zeros((y1 - y0 + 1, strip_height * 4 * (x1 - x0 + 1)), dtype=np.float64)
         check(lib().izpi_render_tile_rows(self._h, strip_height, x0, y0, x1, y1, rows.ctypes.data))
         return rows
+
+    def render_stats(self) -> dict:
+        st = RenderStats()
+        check(lib().izpi_render_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in RenderStats._fields_}
 
     def canvas_device_ptr(self) -> int:
         p = C.c_void_p()

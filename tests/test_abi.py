@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     from izpi_b200 import scene as S
     assert S.PRIM_DTYPE.itemsize == 168 and S.NODE_DTYPE.itemsize == 128
     assert C.sizeof(S.MaterialSpec) == 64 and C.sizeof(S.TextureSpec) == 48 and C.sizeof(S.CameraSpec) == 128
-    assert C.sizeof(cuda.RenderConfig) == 88 and C.sizeof(cuda.TraceStats) == 32
+    assert C.sizeof(cuda.RenderConfig) == 88 and C.sizeof(cuda.TraceStats) == 32 and C.sizeof(cuda.RenderStats) == 56
     from izpi_b200 import proto
     # sizeof() of the same structs compiled from include/izpi_proto.h / izpi_scene.h with gcc
     assert C.sizeof(proto.ProtoOptions) == 72 and C.sizeof(proto.ProtoImage) == 24 and C.sizeof(proto.ProtoSPD) == 32
@@ -49,13 +49,13 @@ def test_headers_compile_as_plain_c(tmp_path):
     import subprocess
     src = tmp_path / "abi.c"
     src.write_text('#include <stdio.h>\n#include "izpi_cuda.h"\n#include "izpi_host.h"\n#include "izpi_proto.h"\n'
-                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(izpi_proto_options), sizeof(izpi_scene_spec), '
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(izpi_render_stats), sizeof(izpi_proto_options), sizeof(izpi_scene_spec), '
                    'sizeof(izpi_prim_rec), sizeof(izpi_tri_attr), sizeof(izpi_bvh4_node), sizeof(izpi_render_config), sizeof(izpi_prim_spec), '
                    'sizeof(izpi_material_spec));return 0;}\n')
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)], text=True).split()
-    assert [int(x) for x in out] == [72, 200, 80, 176, 128, 88, 168, 64]
+    assert [int(x) for x in out] == [56, 72, 200, 80, 176, 128, 88, 168, 64]
 
 
 def _has_gpu():

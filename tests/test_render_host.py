@@ -86,3 +86,75 @@ def test_reduce_canvas_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+# ---- dynamic dealing: the shared tile cursor (renderer.go:126-147: workers pull work units from one channel) -------------
+def _claim_all(cursor_addr, n_tiles, tile_paths, batch_paths, takers):
+    import ctypes as C
+    from izpi_b200 import cuda
+    L = cuda.lib()
+    out = []
+    b, e = C.c_int32(), C.c_int32()
+    while L.izpi_host_claim_tiles(C.c_void_p(cursor_addr), n_tiles, tile_paths, batch_paths, takers, C.byref(b), C.byref(e)):
+        out.append((b.value, e.value))
+    return out
+
+
+def test_claim_policy_single_taker_and_guided():
+    cur = render.TileCursor()
+    try:
+        a = cur.begin_frame(0)
+        assert _claim_all(a, 256, 40000, 1 << 24, 1) == [(0, 256)]  # a private cursor takes the list at once
+        a = cur.begin_frame(0)
+        claims = _claim_all(a, 10800, 768 * 1024, 1 << 24, 16)  # config 5: 786k paths per tile, 21 tiles fill a batch
+        assert claims[0] == (0, 21) and claims[-1][1] == 10800
+        assert all(c[1] - c[0] <= 21 for c in claims) and all(x[1] == y[0] for x, y in zip(claims, claims[1:]))
+        sizes = [c[1] - c[0] for c in claims]
+        assert sizes[-2] <= 4 and min(sizes[:-1]) >= 2  # runs shrink towards the end, never below 2^20 paths
+    finally:
+        cur.close()
+
+
+def _claim_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for frame in range(3):  # several frames: the slots of the cursor are recycled without a barrier
+        w, h = 3840, 2160
+        tiles = render.tile_list(w, h)
+        cur = render.shared_cursor()
+        assert cur is not None
+        addr = cur.begin_frame(rank)
+        mine = _claim_all(addr, len(tiles), 768 * 64, 1 << 20, 2 * world)
+        # stand-in for the render: mark every claimed tile once
+        marks = torch.zeros(len(tiles), dtype=torch.float64)
+        for b, e in mine:
+            marks[b:e] += 1
+        render.reduce_canvas(marks, dst=0)
+        if rank == 0:
+            ok = ok and bool((marks == 1).all())
+    if rank == 0:
+        q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_cursor_world2_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_claim_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
