@@ -48,11 +48,11 @@ typedef struct izpi_proto_image {
   const double* pixels_rgba;
 } izpi_proto_image;
 
-/* An entry of the light-source library (internal/lightsources/lightsources.go:6-466) for
- * SpectralConstantTexture.from_light_source_library.  Built in: the three blackbodies (incandescent_2800k, halogen_3200k,
- * cie_illuminant_a_2856k: spectral.NewBlackbodySPD, spectral.go:275-320) and cie_f1_daylight_fluorescent.  The other 38 keys
- * of the reference's library must be supplied here, otherwise the conversion FAILS (their measured tables are not carried by
- * this library, and substituting something else would change the image).  A name that is in neither place is unknown to the
+/* An extra entry for SpectralConstantTexture.from_light_source_library.  The reference's whole library
+ * (internal/lightsources/lightsources.go:6-466, lookup :468-471) is built in: 39 tabulated SPDs (spectral.NewCIESPD, 75 samples,
+ * 380..750 nm @ 5 nm) and the three blackbodies (incandescent_2800k, halogen_3200k, cie_illuminant_a_2856k:
+ * spectral.NewBlackbodySPD, spectral.go:275-320), so a scene naming any of the 42 keys converts stand-alone.  Entries given
+ * here are looked up FIRST (a deployment with a patched library).  A name that is in neither place is unknown to the
  * reference too, which falls back to CIE illuminant A (transport.go:483-490); so does this library. */
 typedef struct izpi_proto_spd {
   const char* name;

@@ -540,12 +540,7 @@ bool text_message(Lexer& lx, int msg, Node& node, Parsed& P, char closer, int de
 
 // ---------------------------------------------------------------------------------------------------------------
 // (3) ToScene
-const double kCieF1[75] = {  // lightsources.go:230-239 "cie_f1_daylight_fluorescent" (CIE 15 illuminant F1, 380-750 nm @ 5 nm, peak-normalised)
-    0.0350, 0.0380, 0.0430, 0.0500, 0.0590, 0.0710, 0.0870, 0.1090, 0.1390, 0.1800, 0.2360, 0.3130, 0.4190, 0.5660, 0.7730,
-    1.0000, 0.9730, 0.7380, 0.5650, 0.4610, 0.3990, 0.3620, 0.3410, 0.3310, 0.3280, 0.3300, 0.3360, 0.3450, 0.3570, 0.3710,
-    0.3880, 0.4070, 0.4290, 0.4530, 0.4800, 0.5080, 0.5390, 0.5720, 0.6080, 0.6460, 0.6870, 0.7310, 0.7780, 0.8280, 0.8820,
-    0.9380, 0.9980, 1.0000, 0.9860, 0.9420, 0.8740, 0.7900, 0.6960, 0.6000, 0.5060, 0.4200, 0.3430, 0.2780, 0.2240, 0.1800,
-    0.1450, 0.1170, 0.0950, 0.0770, 0.0630, 0.0520, 0.0430, 0.0360, 0.0300, 0.0250, 0.0210, 0.0180, 0.0150, 0.0130, 0.0110};
+#include "lightsources_table.inc"  // the 39 tabulated entries of the reference's library (lightsources.go:6-466), generated data
 
 void blackbody(double temperature, std::vector<double>& w, std::vector<double>& v) {  // spectral.NewBlackbodySPD (spectral.go:275-320)
   const double h = 6.62607015e-34, c = 2.99792458e8, k = 1.380649e-23;
@@ -633,23 +628,15 @@ struct Builder {
       if (name == "incandescent_2800k") blackbody(2800, w, v);
       else if (name == "halogen_3200k") blackbody(3200, w, v);
       else if (name == "cie_illuminant_a_2856k") blackbody(2856, w, v);
-      else if (name == "cie_f1_daylight_fluorescent") { w.resize(75); for (int i = 0; i < 75; i++) w[i] = 380.0 + 5.0 * i; v.assign(kCieF1, kCieF1 + 75); }
       else {
-        // Keys of the reference's library (lightsources.go:6-466) whose measured tables are not carried here: converting them
-        // needs the SPD from the caller.  Any OTHER name is unknown to the reference as well, which then falls back to CIE
-        // illuminant A with a warning (transport.go:483-490; TestLightSourceLibraryIntegration expects success) -- same here.
-        static const char* const kReferenceKeys[] = {
-            "hy_cree_llf_tm_30_90", "hy_ngl_47_tm_30_92", "pc_ngl_124_tm_30_194", "pc_ngl_308_tm_30_231", "pcv_soraa_prem_2700_k_tm_30_294",
-            "pcv_soraa_vivid_2700_k_tm_30_296", "hy_ge_lumination", "pc_maxled", "hy_cree_module", "pc_current_ge", "cm_lumenetix",
-            "cm_acuity_evo_4", "cm_intense_mxrtr2", "pc_samjin", "cm_edison_price_lumenetix", "cm_pathway_lexel", "pc_green_creative_mr16",
-            "pc_soraa_mr16_830", "hy_cree_par38", "pc_seoul_sunlike_3030", "cie_f2_cool_white_fluorescent", "cie_f3_white_fluorescent",
-            "cie_f4_warm_white_fluorescent", "cie_f5_daylight_fluorescent", "cie_f6_lite_white_fluorescent", "cie_f7_broadband_daylight",
-            "cie_f8_broadband_cool_white", "cie_f9_broadband_cool_white_deluxe", "cie_f10_narrowband_5000k", "cie_f11_narrowband_4000k",
-            "cie_f12_narrowband_3000k", "hps_cie238", "hps_c100s54_standard", "hps_sdw_t_100w", "incandescent_halogen_real",
-            "incandescent_krypton_real", "incandescent_60w_a19_real", "laser_red_650nm"};
-        for (const char* k : kReferenceKeys)
-          if (name == k) return fail("light source \"" + name + "\" is not built in; supply its SPD in izpi_proto_options.light_sources");
-        blackbody(2856, w, v);
+        // lightsources.GetLightSource (lightsources.go:468-471) over the tabulated entries.  A name that is not in the library is
+        // unknown to the reference as well, which then falls back to CIE illuminant A with a warning (transport.go:483-490;
+        // TestLightSourceLibraryIntegration expects success) -- same here.
+        const LightSourceEntry* hit = nullptr;
+        for (const LightSourceEntry& e : kLightSources)
+          if (name == e.name) { hit = &e; break; }
+        if (hit) { w.resize(75); for (int i = 0; i < 75; i++) w[i] = 380.0 + 5.0 * i; v.assign(hit->values, hit->values + 75); }
+        else blackbody(2856, w, v);
       }
       out = tabulated(std::move(w), std::move(v));
       return true;

@@ -404,8 +404,6 @@ def test_conversion_errors_mirror_the_reference():
         a = m.materials["a"]; a.name, a.type = "a", 6
         for t in (a.pbr.albedo, a.pbr.roughness, a.pbr.metalness, a.pbr.normal_map):
             _vec3(t.constant.value, (0.5, 0.5, 0.5))
-    def unknown_light(m):
-        a = m.materials["a"]; a.name, a.type = "a", 2; a.diffuselight.spectral_emit.from_light_source_library.light_source_name = "hps_cie238"
     def isotropic(m):
         a = m.materials["a"]; a.name, a.type = "a", 3; _vec3(a.isotropic.albedo.constant.value, (1, 1, 1))
     def displaced_without_map(m):
@@ -416,7 +414,7 @@ def test_conversion_errors_mirror_the_reference():
                     (missing_texture, "texture x.png not found"), (lambert_without_albedo, "lambert material must have either albedo or spectral_albedo"),
                     (dielectric_without_refidx, "dielectric material must have either refidx or spectral_refidx"),
                     (light_without_emit, "diffuse light material must have either emit or spectral_emit"), (checker, "unknown texture type"),
-                    (pbr_without_sss, "unknown texture type"), (unknown_light, "not built in"), (isotropic, "isotropic"),
+                    (pbr_without_sss, "unknown texture type"), (isotropic, "isotropic"),
                     (displaced_without_map, "displacement map d.png not found")]:
         with pytest.raises(cuda.IzpiError) as e:
             scene_with(fn).to_scene()
@@ -516,33 +514,49 @@ def test_reference_pbr_material_transformation(oracle_mod):
         assert 0.0 <= v <= 1.0 and v == lum
 
 
-@pytest.mark.parametrize("name,known", [("incandescent_2800k", True), ("cie_illuminant_a_2856k", True), ("cie_f1_daylight_fluorescent", True),
-                                        ("nonexistent_light_source", True), ("hy_cree_llf_tm_30_90", False), ("cie_f4_warm_white_fluorescent", False)])
-def test_reference_light_source_library_integration(oracle_mod, name, known):
-    """transport_test.go:140-191: every library name -- and an unknown one, which falls back to CIE illuminant A -- gives a
-    spectral texture with values in [0, 1] at 400..700 nm.  Names of the reference's library whose tables this library does not
-    carry must be supplied by the caller; without them the conversion fails instead of substituting."""
+def _library():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "lightsources.json")))
+
+
+def _blackbody(k):
+    """spectral.NewBlackbodySPD (spectral.go:275-320): Planck's law at 380..750 nm @ 5 nm, normalised to its maximum."""
+    h, c, kb = 6.62607015e-34, 2.99792458e8, 1.380649e-23
+    lam = (380.0 + 5.0 * np.arange(75)) * 1e-9
+    v = (2.0 * h * c * c) / (lam ** 5 * (np.exp((h * c / kb) / (lam * k)) - 1.0))
+    return v / v.max()
+
+
+@pytest.mark.parametrize("name", sorted(_library()) + ["nonexistent_light_source"])
+def test_reference_light_source_library_integration(oracle_mod, name):
+    """transport_test.go:140-191, for EVERY key of the reference's library (lightsources.go:6-466) and for an unknown name (which
+    falls back to CIE illuminant A, transport.go:483-490): the conversion succeeds stand-alone, the spectral texture is the
+    library's table sample for sample (tests/golden/lightsources.json, generated from the reference by
+    scripts/gen_lightsources.py), and its values at 400..700 nm are finite and non-negative."""
     m = ps.Scene()
     a = m.materials["l"]; a.name, a.type = "l", 2
     a.diffuselight.spectral_emit.from_light_source_library.light_source_name = name
     s = proto.ProtoScene(m.SerializeToString())
-    if not known:
-        with pytest.raises(cuda.IzpiError):
-            s.to_scene()
-        s = proto.ProtoScene(m.SerializeToString())
-        s.to_scene(light_sources={name: (380.0 + 5.0 * np.arange(75), np.linspace(0.2, 1.0, 75))})
-    else:
-        s.to_scene()
+    s.to_scene()
     _, mats, _, stex = spec_view(s.to_c())
+    d = spectral_desc(stex, mats[0].spectral_tex)
+    lib = _library()
+    want = lib.get(name, {"blackbody_k": 2856.0})
+    want_v = np.asarray(want["values"]) if "values" in want else _blackbody(want["blackbody_k"])
+    got_w, got_v = np.asarray(d[-2]), np.asarray(d[-1])
+    assert np.array_equal(got_w, 380.0 + 5.0 * np.arange(75))
+    if "values" in want:
+        assert np.array_equal(got_v, want_v)
+    else:
+        np.testing.assert_allclose(got_v, want_v, rtol=1e-12)
     osn = oracle_mod.OracleScene(s)
     vals = [osn.spectral_texture_value(mats[0].spectral_tex, lam) for lam in (400.0, 500.0, 600.0, 700.0)]
-    assert all(0.0 <= v <= 1.0 for v in vals)
-    if name == "nonexistent_light_source":  # == illuminant A
-        m2 = ps.Scene()
-        b = m2.materials["l"]; b.name, b.type = "l", 2
-        b.diffuselight.spectral_emit.from_light_source_library.light_source_name = "cie_illuminant_a_2856k"
-        s2 = proto.ProtoScene(m2.SerializeToString()).to_scene()
-        assert spectral_desc(spec_view(s2.to_c())[3], 0) == spectral_desc(stex, 0)
+    assert all(np.isfinite(x) and x >= 0.0 for x in vals)
+    # a caller-supplied entry of the same name wins (a deployment with a patched library)
+    s2 = proto.ProtoScene(m.SerializeToString())
+    s2.to_scene(light_sources={name: (380.0 + 5.0 * np.arange(75), np.linspace(0.2, 1.0, 75))})
+    d2 = spectral_desc(spec_view(s2.to_c())[3], 0)
+    assert np.array_equal(np.asarray(d2[-1]), np.linspace(0.2, 1.0, 75))
 
 
 def test_reference_spectral_texture_methods(oracle_mod):
