@@ -189,6 +189,12 @@ int izpi_bvh4_build_fetch(izpi_ctx* ctx, izpi_bvh4_node* nodes, int32_t* perm);
 int izpi_debug_ray_aabb4(izpi_ctx* ctx, int32_t n, const float* org, const float* inv, const float* bounds,
                          const float* tmax, uint8_t* masks);
 
+/* Diagnostic: hitable.Hitable.Hit with the full hitrecord.HitRecord (hitrecord.go:6-12) for n rays against the uploaded world:
+ * prim_id[i] = original index or -1, out9 = t u v p.xyz normal.xyz (zeros on a miss) -- what shading consumes, so that the
+ * reference's exact records (triangle_test.go:69-134: normal 0.8908708063747479, ...) can be checked on the device. */
+int izpi_debug_hit(izpi_ctx* ctx, int32_t n, const double* org, const double* dir, double tmin, double tmax, int32_t* prim_id,
+                   double* out9);
+
 /* Diagnostic: measured dependent-FMA throughput (TFLOP/s, 2 flops per FMA) of the fp32 (fp64 = 0) or fp64 (fp64 = 1) vector
  * pipe of the context's device: the FLOP side of the traversal roofline (BASELINE north_star). */
 int izpi_debug_fma_peak(izpi_ctx* ctx, int fp64, double* tflops);

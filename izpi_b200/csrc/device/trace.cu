@@ -276,6 +276,31 @@ __global__ void box4_kernel(int n, const float* __restrict__ org, const float* _
 }
 
 
+// Diagnostic: world.Hit with the FULL hit record (hitrecord.HitRecord: t, u, v, p, normal), one thread per ray, so that the
+// reference's Triangle.Hit records (triangle_test.go:69-134) can be replayed on the device field by field.
+__global__ void debug_hit_kernel(const __grid_constant__ DScene sc, int n, const double* __restrict__ org, const double* __restrict__ dir,
+                                 double tmin, double tmax, int32_t* __restrict__ ids, double* __restrict__ out9) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  DRay r;
+  r.o = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
+  r.d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+  r.time = 0; r.lambda = 0;
+  int32_t stack[kStackDepth];
+  uint32_t a = 0, b = 0;
+  double t = 0;
+  int rec = world_closest<false>(sc, r, tmin, tmax, t, stack, 1, a, b);
+  double* o = out9 + 9 * (size_t)i;
+  for (int k = 0; k < 9; k++) o[k] = 0.0;
+  ids[i] = -1;
+  if (rec < 0) return;
+  PrimRec pr = load_rec(sc.prims + rec);
+  DHit h;
+  if (!prim_hit<true>(sc, rec, pr, r, tmin, tmax, h)) return;
+  ids[i] = pr.orig_id;
+  o[0] = h.t; o[1] = h.u; o[2] = h.v; o[3] = h.p.x; o[4] = h.p.y; o[5] = h.p.z; o[6] = h.n.x; o[7] = h.n.y; o[8] = h.n.z;
+}
+
 // Diagnostic: dependent-FMA throughput of the fp32 / fp64 vector pipes (the FLOP side of the traversal
 // roofline; MEASURED_PEAKS.json carries HBM and tensor-core peaks only).  16 independent chains per thread.
 template <typename T>
@@ -481,6 +506,32 @@ int izpi_debug_ray_aabb4(izpi_ctx* ctx, int32_t n, const float* org, const float
   return IZPI_OK;
 }
 
+
+int izpi_debug_hit(izpi_ctx* ctx, int32_t n, const double* org, const double* dir, double tmin, double tmax, int32_t* prim_id, double* out9) {
+  if (!ctx || n <= 0 || !org || !dir || !prim_id || !out9) { set_error("izpi_debug_hit: bad argument"); return IZPI_EINVAL; }
+  if (!ctx->has_scene) { set_error("izpi_debug_hit: no scene uploaded"); return IZPI_ESTATE; }
+  if (!ctx->scene.attrs && ctx->scene.n_prims > 0) { set_error("izpi_debug_hit: scene was uploaded without tri_attrs"); return IZPI_ESTATE; }
+  IZ_CUDA(cudaSetDevice(ctx->device));
+  double *d_o = nullptr, *d_d = nullptr, *d_out = nullptr;
+  int32_t* d_ids = nullptr;
+  cudaError_t e = cudaMalloc(&d_o, (size_t)n * 24);
+  if (e == cudaSuccess) e = cudaMalloc(&d_d, (size_t)n * 24);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * 72);
+  if (e == cudaSuccess) e = cudaMalloc(&d_ids, (size_t)n * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d_o, org, (size_t)n * 24, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_d, dir, (size_t)n * 24, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    debug_hit_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->scene, n, d_o, d_d, tmin, tmax, d_ids, d_out);
+    e = cudaGetLastError();
+    ctx->launches++;
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(prim_id, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out9, d_out, (size_t)n * 72, cudaMemcpyDeviceToHost);
+  cudaFree(d_o); cudaFree(d_d); cudaFree(d_out); cudaFree(d_ids);
+  if (e != cudaSuccess) { set_error(std::string("izpi_debug_hit: ") + cudaGetErrorString(e)); return IZPI_ECUDA; }
+  return IZPI_OK;
+}
 
 int izpi_debug_fma_peak(izpi_ctx* ctx, int fp64, double* tflops) {
   if (!ctx || !tflops) { set_error("izpi_debug_fma_peak: bad argument"); return IZPI_EINVAL; }

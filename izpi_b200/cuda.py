@@ -51,7 +51,7 @@ EXPORTS = [
     "izpi_scene_image_size", "izpi_scene_image_export", "izpi_scene_image_adopt", "izpi_scene_image_commit",
     "izpi_render_tiles_shared", "izpi_render_get_stats",
     "izpi_trace_closest", "izpi_trace_closest_device", "izpi_launch_count", "izpi_render_setup", "izpi_render_tiles", "izpi_render_tile_rows",
-    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_debug_fma_peak", "izpi_displace", "izpi_displace_fetch", "izpi_bvh4_build", "izpi_bvh4_build_fetch",
+    "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_debug_hit", "izpi_debug_fma_peak", "izpi_displace", "izpi_displace_fetch", "izpi_bvh4_build", "izpi_bvh4_build_fetch",
     "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
     "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
     "izpi_host_tiles", "izpi_host_render", "izpi_host_claim_tiles",
@@ -86,6 +86,7 @@ def lib():
     L.izpi_launch_count.argtypes = [C.c_void_p]
     L.izpi_launch_count.restype = C.c_uint64
     L.izpi_debug_ray_aabb4.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.izpi_debug_hit.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
     L.izpi_debug_fma_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.izpi_displace.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_double,
                                 C.c_int, C.POINTER(C.c_int64)]
@@ -272,6 +273,15 @@ class Context:
         v = C.c_double()
         check(lib().izpi_debug_fma_peak(self._h, int(fp64), C.byref(v)))
         return v.value
+
+    def debug_hit(self, org, direction, tmin=0.0, tmax=np.finfo(np.float64).max):
+        """world.Hit with the full HitRecord: (ids, records (n, 9) = t u v p.xyz normal.xyz)."""
+        o = np.ascontiguousarray(org, dtype=np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(direction, dtype=np.float64).reshape(-1, 3)
+        ids = np.zeros(len(o), dtype=np.int32)
+        out = np.zeros((len(o), 9), dtype=np.float64)
+        check(lib().izpi_debug_hit(self._h, len(o), o.ctypes.data, d.ctypes.data, tmin, tmax, ids.ctypes.data, out.ctypes.data))
+        return ids, out
 
     def debug_ray_aabb4(self, org, inv, bounds, tmax):
         o = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)

@@ -34,7 +34,7 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
                 ("sampler", C.c_int32), ("rng_mode", C.c_int32), ("flavour", C.c_int32), ("threads", C.c_int32),
                 ("seed", C.c_uint64), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
-                ("epilogue", C.c_int32), ("reserved", C.c_int32)]
+                ("epilogue", C.c_int32), ("libm_jitter", C.c_int32)]
 
 
 _lib = None
@@ -74,6 +74,7 @@ def lib():
         L.oracle_trace.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                    C.c_void_p, C.c_void_p, C.POINTER(Stats), C.c_int]
         L.oracle_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_render_tile.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_firefly_rejection.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.oracle_xyz_to_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double]
         L.oracle_apply_displacement.restype = C.c_int64
@@ -207,12 +208,21 @@ class OracleScene:
         return lib().oracle_spectral_texture_value(self._h, tex, lam)
 
     def render(self, width, height, spp, max_depth=50, sampler=0, rng_mode=0, flavour=0, threads=None, seed=1,
-               window=None, epilogue=True):
+               window=None, epilogue=True, libm_jitter=0):
         x0, y0, x1, y1 = window if window is not None else (0, 0, width - 1, height - 1)
         p = RenderParams(width=width, height=height, spp=spp, max_depth=max_depth, sampler=sampler,
                          rng_mode=rng_mode, flavour=flavour, threads=threads or os.cpu_count() or 1, seed=seed,
-                         x0=x0, y0=y0, x1=x1, y1=y1, epilogue=int(epilogue))
+                         x0=x0, y0=y0, x1=x1, y1=y1, epilogue=int(epilogue), libm_jitter=int(libm_jitter))
         canvas = np.zeros((height, width, 4), dtype=np.float64)
         rays = C.c_uint64()
         lib().oracle_render(self._h, C.byref(p), canvas.ctypes.data, C.byref(rays))
         return canvas, rays.value
+
+    def render_tile(self, width, height, spp, x0, y0, x1, y1, strip_height=1, max_depth=50, sampler=0, rng_mode=0, seed=1):
+        """worker.RenderTile (internal/worker/render.go:17-75): the rows a worker streams back for one tile."""
+        p = RenderParams(width=width, height=height, spp=spp, max_depth=max_depth, sampler=sampler, rng_mode=rng_mode, flavour=0,
+                         threads=1, seed=seed, x0=0, y0=0, x1=0, y1=0, epilogue=0, libm_jitter=0)
+        rows = np.zeros((y1 - y0 + 1, strip_height * 4 * (x1 - x0 + 1)), dtype=np.float64)
+        rays = C.c_uint64()
+        lib().oracle_render_tile(self._h, C.byref(p), strip_height, x0, y0, x1, y1, rows.ctypes.data, C.byref(rays))
+        return rows, rays.value

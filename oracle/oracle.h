@@ -69,11 +69,16 @@ typedef struct oracle_render_params {
   uint64_t seed;
   int32_t x0, y0, x1, y1; /* pixel window to render, inclusive (reference's workUnit); full image = 0,0,W-1,H-1 */
   int32_t epilogue;       /* spectral only: run FireflyRejection + XYZToRGB (renderer.go:216-219) */
-  int32_t reserved;
+  int32_t libm_jitter;    /* 0 = off.  != 0: every libm result on the path is moved by up to +-2 ulp, keyed by this seed: the
+                             sensitivity probe that classifies the pixels on which device and oracle may differ (oracle_geom.hpp) */
 } oracle_render_params;
 
 /* canvas: 4*W*H doubles, Float64NRGBA layout (y*W+x)*4+c, reference row flip (rgb.go:41) */
 void oracle_render(const oracle_scene* s, const oracle_render_params* p, double* canvas, uint64_t* num_rays);
+/* worker.RenderTile (internal/worker/render.go:17-75): (y1-y0+1) rows of strip_height*4*(x1-x0+1) doubles, row r = image row
+ * y0 + r (no flip), first 4*(x1-x0+1) doubles = {X,Y,Z,1} pixel means, rest zero.  The window fields of p are ignored. */
+void oracle_render_tile(const oracle_scene* s, const oracle_render_params* p, uint32_t strip_height, uint32_t x0, uint32_t y0,
+                        uint32_t x1, uint32_t y1, double* rows, uint64_t* num_rays);
 void oracle_firefly_rejection(double* canvas, int32_t width, int32_t height);      /* firefly_rejection.go:12 */
 void oracle_xyz_to_rgb(const double* in, double* out, int32_t width, int32_t height, double exposure); /* rgb_image.go:28 */
 void oracle_tiles(int32_t size_x, int32_t size_y, int32_t* step_x, int32_t* step_y);  /* common/tiles.go:6 */

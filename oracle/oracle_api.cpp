@@ -222,8 +222,63 @@ void oracle_tiles(int32_t sx, int32_t sy, int32_t* stepx, int32_t* stepy) {  // 
   for (int s : sizes) if (sy % s == 0) { *stepy = s; break; }
 }
 
+// One pixel of renderRectRGB (render/rgb.go:27-41) / RenderPixelSpectral (render/spectral.go:75-106) / the AOV samplers:
+// spp samples, mean.  rng / camRng are the work unit's LCGs (mode 0); mode 1 replays the device's counter RNG.
+static void render_pixel(const oracle_scene* s, const oracle_render_params* p, const Camera& cam, Sampler& smp, int x, int y, Rng& rng,
+                         Rng& camRng, double out[3]) {
+  const int nx = p->width, ny = p->height;
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (int smpl = 0; smpl < p->spp; smpl++) {
+    Rng* r = &rng; Rng* cr = &camRng;
+    Rng ctr;
+    if (p->rng_mode == 1) {
+      ctr.mode = 1; ctr.key = Rng::stream_key(p->seed, (uint64_t)y * (uint64_t)nx + (uint64_t)x, (uint64_t)smpl); ctr.ctr = 0;
+      r = &ctr; cr = &ctr;
+    }
+    if (p->sampler >= 2) {  // sampler/albedo.go:30-36, sampler/normal.go:28-34 through the RGB pixel loop
+      double u = ((double)x + r->Float64()) / (double)nx;
+      double v = ((double)y + r->Float64()) / (double)ny;
+      Ray ray = cam.GetRay(u, v, 0, *cr);
+      smp.numRays++;
+      HitRecord rec; const Material* mat;
+      Vec3 c;
+      if (s->world.Hit(ray, 0.001, DBL_MAX, rec, mat)) c = p->sampler == 2 ? mat->Albedo(rec.u, rec.v) : rec.normal;
+      c = DeNAN(c);
+      a0 = a0 + c.X; a1 = a1 + c.Y; a2 = a2 + c.Z;
+    } else if (p->sampler == 0) {  // rgb.go:30-37
+      double u = ((double)x + r->Float64()) / (double)nx;
+      double v = ((double)y + r->Float64()) / (double)ny;
+      Ray ray = cam.GetRay(u, v, 0, *cr);
+      Vec3 c = DeNAN(smp.Sample(ray, &s->world, &s->lights, 0, *r));
+      a0 = a0 + c.X; a1 = a1 + c.Y; a2 = a2 + c.Z;
+    } else {  // render/spectral.go:75-96
+      double lambda, pdf;
+      SampleWavelength(r->Float64(), lambda, pdf);
+      if (pdf == 0) continue;
+      double u = ((double)x + r->Float64()) / (double)nx;
+      double v = ((double)y + r->Float64()) / (double)ny;
+      Ray ray = cam.GetRay(u, v, lambda, *cr);
+      double radiance = smp.SampleSpectral(ray, &s->world, &s->lights, 0, *r);
+      double cx, cy, cz;
+      GetCIEValues(lambda, cx, cy, cz);
+      a0 += (radiance * cx) / pdf; a1 += (radiance * cy) / pdf; a2 += (radiance * cz) / pdf;
+    }
+  }
+  if (p->sampler != 1) { a0 = a0 / (double)p->spp; a1 = a1 / (double)p->spp; a2 = a2 / (double)p->spp; }  // rgb.go:39
+  else { double inv = 1.0 / (double)p->spp; a0 = a0 * inv; a1 = a1 * inv; a2 = a2 * inv; }             // spectral.go:99-103
+  out[0] = a0; out[1] = a1; out[2] = a2;
+}
+
+static void init_sampler(Sampler& smp, const oracle_render_params* p) {
+  smp.maxDepth = p->max_depth;
+  smp.background = Vec3();  // colours.Black
+  smp.spectralBackground.wavelengths = {380, 750};  // colours.SpectralBlack (colours.go:19): all-zero SPD
+  smp.spectralBackground.values = {0, 0};
+}
+
 void oracle_render(const oracle_scene* s, const oracle_render_params* p, double* canvas, uint64_t* num_rays) {
   if (s->bvh) s->bvh->flavour = p->flavour;
+  g_oracle_libm_jitter = p->libm_jitter;
   const int nx = p->width, ny = p->height;
   int threads = p->threads < 1 ? 1 : p->threads;
   std::atomic<int> nextRow(p->y0);
@@ -232,10 +287,7 @@ void oracle_render(const oracle_scene* s, const oracle_render_params* p, double*
   Camera cam = s->camera;
   auto work = [&]() {
     Sampler smp;
-    smp.maxDepth = p->max_depth;
-    smp.background = Vec3();  // colours.Black
-    smp.spectralBackground.wavelengths = {380, 750};  // colours.SpectralBlack (colours.go:19): all-zero SPD
-    smp.spectralBackground.values = {0, 0};
+    init_sampler(smp, p);
     for (;;) {
       int y = nextRow.fetch_add(1);
       if (y > p->y1) break;
@@ -243,49 +295,12 @@ void oracle_render(const oracle_scene* s, const oracle_render_params* p, double*
       rng.mode = 0; rng.state = Rng::mix64(p->seed + 0x1000003ull * (uint64_t)y) & 0xffffffffull;
       camRng.mode = 0; camRng.state = Rng::mix64(p->seed ^ (0xC0FFEEull + (uint64_t)y)) & 0xffffffffull;
       for (int x = p->x0; x <= p->x1; x++) {
-        double a0 = 0, a1 = 0, a2 = 0;
-        for (int smpl = 0; smpl < p->spp; smpl++) {
-          Rng* r = &rng; Rng* cr = &camRng;
-          Rng ctr;
-          if (p->rng_mode == 1) {
-            ctr.mode = 1; ctr.key = Rng::stream_key(p->seed, (uint64_t)y * (uint64_t)nx + (uint64_t)x, (uint64_t)smpl); ctr.ctr = 0;
-            r = &ctr; cr = &ctr;
-          }
-          if (p->sampler >= 2) {  // sampler/albedo.go:30-36, sampler/normal.go:28-34 through the RGB pixel loop
-            double u = ((double)x + r->Float64()) / (double)nx;
-            double v = ((double)y + r->Float64()) / (double)ny;
-            Ray ray = cam.GetRay(u, v, 0, *cr);
-            smp.numRays++;
-            HitRecord rec; const Material* mat;
-            Vec3 c;
-            if (s->world.Hit(ray, 0.001, DBL_MAX, rec, mat)) c = p->sampler == 2 ? mat->Albedo(rec.u, rec.v) : rec.normal;
-            c = DeNAN(c);
-            a0 = a0 + c.X; a1 = a1 + c.Y; a2 = a2 + c.Z;
-          } else if (p->sampler == 0) {  // rgb.go:30-37
-            double u = ((double)x + r->Float64()) / (double)nx;
-            double v = ((double)y + r->Float64()) / (double)ny;
-            Ray ray = cam.GetRay(u, v, 0, *cr);
-            Vec3 c = DeNAN(smp.Sample(ray, &s->world, &s->lights, 0, *r));
-            a0 = a0 + c.X; a1 = a1 + c.Y; a2 = a2 + c.Z;
-          } else {  // render/spectral.go:75-96
-            double lambda, pdf;
-            SampleWavelength(r->Float64(), lambda, pdf);
-            if (pdf == 0) continue;
-            double u = ((double)x + r->Float64()) / (double)nx;
-            double v = ((double)y + r->Float64()) / (double)ny;
-            Ray ray = cam.GetRay(u, v, lambda, *cr);
-            double radiance = smp.SampleSpectral(ray, &s->world, &s->lights, 0, *r);
-            double cx, cy, cz;
-            GetCIEValues(lambda, cx, cy, cz);
-            a0 += (radiance * cx) / pdf; a1 += (radiance * cy) / pdf; a2 += (radiance * cz) / pdf;
-          }
-        }
-        if (p->sampler != 1) { a0 = a0 / (double)p->spp; a1 = a1 / (double)p->spp; a2 = a2 / (double)p->spp; }  // rgb.go:39
-        else { double inv = 1.0 / (double)p->spp; a0 = a0 * inv; a1 = a1 * inv; a2 = a2 * inv; }             // spectral.go:99-103
+        double a[3];
+        render_pixel(s, p, cam, smp, x, y, rng, camRng, a);
         int row = ny - y;  // rgb.go:41: canvas.Set(x, ny-y, ...); row ny is out of bounds -> dropped
         if (row >= 0 && row < ny) {
           double* px = canvas + ((size_t)row * nx + x) * 4;
-          px[0] = a0; px[1] = a1; px[2] = a2; px[3] = 1.0;
+          px[0] = a[0]; px[1] = a[1]; px[2] = a[2]; px[3] = 1.0;
         }
       }
     }
@@ -295,12 +310,42 @@ void oracle_render(const oracle_scene* s, const oracle_render_params* p, double*
   for (int i = 1; i < threads; i++) th.emplace_back(work);
   work();
   for (auto& x : th) x.join();
+  g_oracle_libm_jitter = 0;
   if (num_rays) *num_rays = rays.load();
   if (p->sampler == 1 && p->epilogue) {  // renderer.go:216-219
     oracle_firefly_rejection(canvas, nx, ny);
     std::vector<double> tmp(canvas, canvas + (size_t)4 * nx * ny);
     oracle_xyz_to_rgb(tmp.data(), canvas, nx, ny, cam.exposure);
   }
+}
+
+// worker.RenderTile (internal/worker/render.go:17-75): one LCG from the pool for the whole tile (:24), per image row a fresh
+// strip of stripSize doubles (:35) whose first 4*width entries receive the pixel means and alpha 1 (:51-55); rows are streamed in
+// image order, y0 first, without the local path's row flip, and y == 0 is streamed like any other row.
+void oracle_render_tile(const oracle_scene* s, const oracle_render_params* p, uint32_t strip_height, uint32_t x0, uint32_t y0,
+                        uint32_t x1, uint32_t y1, double* rows, uint64_t* num_rays) {
+  if (s->bvh) s->bvh->flavour = p->flavour;
+  g_oracle_libm_jitter = p->libm_jitter;
+  const size_t stripSize = (size_t)strip_height * 4 * (x1 - x0 + 1);
+  Camera cam = s->camera;
+  Sampler smp;
+  init_sampler(smp, p);
+  Rng rng, camRng;
+  rng.mode = 0; rng.state = Rng::mix64(p->seed + 0x1000003ull * (uint64_t)y0 + x0) & 0xffffffffull;
+  camRng.mode = 0; camRng.state = Rng::mix64(p->seed ^ (0xC0FFEEull + (uint64_t)y0)) & 0xffffffffull;
+  for (uint32_t y = y0; y <= y1; y++) {
+    double* pixels = rows + (size_t)(y - y0) * stripSize;
+    for (size_t k = 0; k < stripSize; k++) pixels[k] = 0.0;  // make([]float64, stripSize)
+    size_t i = 0;
+    for (uint32_t x = x0; x <= x1; x++) {
+      double a[3];
+      render_pixel(s, p, cam, smp, (int)x, (int)y, rng, camRng, a);
+      pixels[i] = a[0]; pixels[i + 1] = a[1]; pixels[i + 2] = a[2]; pixels[i + 3] = 1.0;
+      i += 4;
+    }
+  }
+  g_oracle_libm_jitter = 0;
+  if (num_rays) *num_rays = smp.numRays;
 }
 
 void oracle_firefly_rejection(double* pix, int32_t width, int32_t height) {  // firefly_rejection.go:12-113

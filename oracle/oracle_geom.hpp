@@ -10,12 +10,33 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <cfloat>
 #include <limits>
 #include <memory>
 #include <vector>
 
 #include "../include/izpi_scene.h"
+
+// ---- libm sensitivity probe (tests only) -------------------------------------------------------------------------------
+// The device's sin / cos / pow / exp / atan2 / asin are not correctly rounded (CUDA documents 1-2 ulp), glibc's mostly are.
+// A last-bit difference in a scatter direction is invisible at 1e-7 -- unless the path is chaotic (a chain of bounces
+// between glass spheres multiplies a perturbation by ~10-100x per bounce) or a comparison sits within an ulp of its
+// threshold.  To CLASSIFY the pixels on which the device and the oracle may legitimately differ, the oracle can perturb
+// every libm result on the path by up to +-2 ulp, pseudo-randomly: pixels whose value survives that are stable, and on
+// those the device must agree (tests/test_render_gpu.py).  0 = off (the default, and the only mode that restates the reference).
+extern int g_oracle_libm_jitter;
+inline double LM(double v) {
+  if (g_oracle_libm_jitter == 0 || !(v == v) || v == 0.0 || std::isinf(v)) return v;
+  uint64_t b;
+  std::memcpy(&b, &v, 8);
+  uint64_t h = (b ^ (uint64_t)g_oracle_libm_jitter * 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 29;
+  int k = (int)(h % 5) - 2;  // -2 .. +2 ulp
+  b += (uint64_t)(int64_t)k;
+  std::memcpy(&v, &b, 8);
+  return v;
+}
 
 namespace orc {
 
@@ -236,8 +257,8 @@ struct Triangle : Hitable {
 
 // ---------------------------------------------------------------- Sphere (hitable/sphere.go)
 inline void getSphereUV(const Vec3& p, double& u, double& v) {  // sphere.go:29-35
-  double phi = std::atan2(p.Z, p.X);
-  double theta = std::asin(p.Y);
+  double phi = LM(std::atan2(p.Z, p.X));
+  double theta = LM(std::asin(p.Y));
   u = 1.0 - (phi + M_PI) / (2.0 * M_PI);
   v = (theta + M_PI / 2.0) / M_PI;
 }
@@ -255,8 +276,8 @@ inline Vec3 RandomToSphere(double radius, double distanceSquared, Rng& rng) {  /
   double r1 = rng.Float64(), r2 = rng.Float64();
   double z = 1 + r2 * (std::sqrt(1 - radius * radius / distanceSquared) - 1);
   double phi = 2 * M_PI * r1;
-  double x = std::cos(phi) * std::sqrt(1 - z * z);
-  double y = std::sin(phi) * std::sqrt(1 - z * z);
+  double x = LM(std::cos(phi)) * std::sqrt(1 - z * z);
+  double y = LM(std::sin(phi)) * std::sqrt(1 - z * z);
   return V(x, y, z);
 }
 struct Sphere : Hitable {

@@ -98,15 +98,15 @@ struct SpectralTexture {  // texture/spectral_constant.go
     double spectralValue = 0;
     if (wavelength >= 580.0 && wavelength <= 750.0) {
       double distance = std::fabs(wavelength - 650.0), width = 60.0;
-      spectralValue += r * std::exp(-(distance * distance) / (2.0 * width * width));
+      spectralValue += r * LM(std::exp(-(distance * distance) / (2.0 * width * width)));
     }
     if (wavelength >= 480.0 && wavelength <= 620.0) {
       double distance = std::fabs(wavelength - 550.0), width = 60.0;
-      spectralValue += g * std::exp(-(distance * distance) / (2.0 * width * width));
+      spectralValue += g * LM(std::exp(-(distance * distance) / (2.0 * width * width)));
     }
     if (wavelength >= 380.0 && wavelength <= 520.0) {
       double distance = std::fabs(wavelength - 450.0), width = 60.0;
-      spectralValue += b * std::exp(-(distance * distance) / (2.0 * width * width));
+      spectralValue += b * LM(std::exp(-(distance * distance) / (2.0 * width * width)));
     }
     if (std::fabs(r - g) < 0.15 && std::fabs(g - b) < 0.15 && std::fabs(r - b) < 0.15) {
       double maxRGB = gomax(r, gomax(g, b));
@@ -126,8 +126,8 @@ struct SpectralTexture {  // texture/spectral_constant.go
       return rgbToSpectralValue(rgb.X, rgb.Y, rgb.Z, 380.0 + 5.0 * idx);
     }
     if (type == IZPI_SPEC_TABULATED) return interpolateSPD(lambda);
-    double exponent = -std::pow((lambda - centre) / width, 2);
-    return peak * std::exp(exponent);
+    double exponent = -LM(std::pow((lambda - centre) / width, 2));
+    return peak * LM(std::exp(exponent));
   }
   double interpolateSPD(double lambda) const {  // spectral_constant.go:78-106
     const auto& w = spd.wavelengths; const auto& val = spd.values;
@@ -176,14 +176,14 @@ inline bool refract(const Vec3& v, const Vec3& n, double niOverNt, Vec3& out) { 
 inline double schlick(double cosine, double refIdx) {  // material.go:39
   double r0 = (1.0 - refIdx) / (1.0 + refIdx);
   r0 = r0 * r0;
-  return r0 + (1.0 - r0) * std::pow((1.0 - cosine), 5);
+  return r0 + (1.0 - r0) * LM(std::pow((1.0 - cosine), 5));
 }
 inline Vec3 RandomCosineDirection(Rng& rng) {  // vec3.go:119-127 (note the factor 2 on x,y)
   double r1 = rng.Float64(), r2 = rng.Float64();
   double z = std::sqrt(1 - r2);
   double phi = 2 * M_PI * r1;
-  double x = std::cos(phi) * 2 * std::sqrt(r2);
-  double y = std::sin(phi) * 2 * std::sqrt(r2);
+  double x = LM(std::cos(phi)) * 2 * std::sqrt(r2);
+  double y = LM(std::sin(phi)) * 2 * std::sqrt(r2);
   return V(x, y, z);
 }
 
@@ -269,7 +269,7 @@ struct Material {
     ONB uvw; uvw.BuildFromW(normal);
     Vec3 reflected = reflect(UnitVector(r.direction), normal);
     double cosTheta = std::fabs(Dot(UnitVector(r.direction), normal));
-    double fresnel = 0.04 + (1.0 - 0.04) * std::pow(1.0 - cosTheta, 5.0);
+    double fresnel = 0.04 + (1.0 - 0.04) * LM(std::pow(1.0 - cosTheta, 5.0));
     fresnel = fresnel + (metalnessValue * 0.5);
     double specularProbability = fresnel * (1.0 - roughnessValue);
     Vec3 finalDir;
@@ -303,7 +303,7 @@ struct Material {
         Ray scattered = dielectricCommon(r, hr, rng, this->s, isReflected);
         if (computeBeerLambert && !(v.X == 0 && v.Y == 0 && v.Z == 0) && !isReflected) {
           double pathLength = calculatePathLength(r, hr, scattered);
-          s.attenuation = V(std::exp(-v.X * pathLength), std::exp(-v.Y * pathLength), std::exp(-v.Z * pathLength));
+          s.attenuation = V(LM(std::exp(-v.X * pathLength)), LM(std::exp(-v.Y * pathLength)), LM(std::exp(-v.Z * pathLength)));
         } else {
           s.attenuation = V(1.0, 1.0, 1.0);
         }
@@ -333,7 +333,7 @@ struct Material {
         double albedo;
         if (!isReflected) {
           double pathLength = calculatePathLength(r, hr, scattered);
-          albedo = spectralAbsorption ? std::exp(-spectralAbsorption->Value(lambda, hr.u, hr.v) * pathLength) : 1.0;  // :106-114
+          albedo = spectralAbsorption ? LM(std::exp(-spectralAbsorption->Value(lambda, hr.u, hr.v) * pathLength)) : 1.0;  // :106-114
         } else {
           albedo = 1.0;
         }

@@ -61,16 +61,52 @@ def test_box_golden_on_device(ctx, oracle_mod):
 
 
 def test_triangle_golden_on_device(ctx, oracle_mod):
+    """triangle_test.go:69-134 on the device, the whole hitrecord.HitRecord: t, u, v, p and the exact normal
+    (0.8908708063747479, -0.44543540318737396, 0.0890870806374748), through the slice world and the BVH4 world."""
     from test_oracle_golden import TRI_HITS, _one_tri
     for bvh in (False, True):
         for _, tri, org, d, want in TRI_HITS:
             hs = cuda.HostScene(_one_tri(*tri, bvh=bvh))
             ctx.upload(hs)
             ids, t = ctx.trace_closest([org], [d], 0.0, DMAX)
+            hid, rec = ctx.debug_hit([org], [d], 0.0, DMAX)
             if want is None:
-                assert ids[0] == -1
+                assert ids[0] == -1 and hid[0] == -1
             else:
                 assert ids[0] == 0 and t[0] == want["t"]
+                assert hid[0] == 0 and rec[0, 0] == want["t"] and rec[0, 1] == want["u"] and rec[0, 2] == want["v"]
+                np.testing.assert_array_equal(rec[0, 3:6], want["p"])
+                np.testing.assert_array_equal(rec[0, 6:9], want["normal"])
+
+
+def test_full_hit_records_match_oracle(ctx, oracle_mod):
+    """Full hit records (t, u, v, p, normal) of every primitive kind and wrapper, device vs oracle, bit for bit except where the
+    record passes through atan2 / asin (sphere UVs: the device's libm is within 2 ulp of glibc's, not identical)."""
+    sc = scenes.cornell_box(1.0)
+    sc.world_kind = S.WORLD_BVH4
+    sc.sphere((400, 60, 150), 60, sc.metal((0.8, 0.85, 0.88), 0.1))
+    verts, uvs = scenes.torus_mesh(30, 20, centre=(278.0, 278.0, 278.0), major=120.0, minor=40.0, amp=10.0)
+    sc.triangles(verts, sc.lambertian(sc.constant_texture((0.5, 0.5, 0.5))), uvs)
+    ctx.upload(cuda.HostScene(sc))
+    osn = oracle_mod.OracleScene(sc)
+    org, d = scenes.random_rays(4000, (0, 0, 0), (555, 555, 555))
+    ids, rec = ctx.debug_hit(org, d, 0.001, DMAX)
+    n_sphere = 0
+    for i in range(len(org)):
+        got = osn.hit(org[i], d[i], 0.001, DMAX)
+        if got is None:
+            assert ids[i] == -1
+            continue
+        assert ids[i] == got["prim"]
+        assert rec[i, 0] == got["t"]
+        np.testing.assert_array_equal(rec[i, 3:6], got["p"])
+        np.testing.assert_array_equal(rec[i, 6:9], got["normal"])
+        if sc.prims["type"][got["prim"]] == S.PRIM_SPHERE:
+            n_sphere += 1
+            np.testing.assert_allclose(rec[i, 1:3], [got["u"], got["v"]], rtol=0, atol=4e-16)
+        else:
+            assert rec[i, 1] == got["u"] and rec[i, 2] == got["v"]
+    assert n_sphere > 20 and (ids >= 0).mean() > 0.5
 
 
 @pytest.mark.parametrize("shape,nrays", [((40, 25), 1 << 14), ((300, 200), 1 << 17)])
