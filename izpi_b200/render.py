@@ -123,6 +123,9 @@ def shared_cursor():
             if _cursor:
                 _cursor.close()
             _cursor = False
+        if _cursor:
+            import atexit
+            atexit.register(_cursor.close)
     return _cursor or None
 
 

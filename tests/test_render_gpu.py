@@ -269,4 +269,4 @@ def test_worker_tile_rows(ctx, oracle_mod):
     with pytest.raises(cuda.IzpiError):
         ctx.render_tile_rows(0, 0, 24, 24, strip_height=0)
     with pytest.raises(cuda.IzpiError):
-        ctx.render_tile_rows(0, 0, 50, 24)
+        ctx.render_tile_rows(0, 0, 64, 24)  # x1 outside the 64-pixel-wide image
