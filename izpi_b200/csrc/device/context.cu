@@ -258,6 +258,7 @@ static int upload_one(izpi_ctx* ctx, const izpi_scene_desc* d) {
       return IZPI_EINVAL;
     }
   }
+  s.scalar_need = need_scalar;
   for (int i = 0; i < d->n_prims; i++) {
     const int m = (int)((d->prims[i].tag >> 4) & 0x3fffu);
     if (d->n_materials > 0 && m >= d->n_materials) { set_error("izpi_scene_upload: primitive record refers to a missing material"); return IZPI_EINVAL; }
@@ -359,6 +360,20 @@ static int upload_one(izpi_ctx* ctx, const izpi_scene_desc* d) {
   if ((rc = upload(ctx, d->xforms, (size_t)d->n_xforms, &s.xforms)) != IZPI_OK) return rc;
   if ((rc = upload(ctx, d->lights, (size_t)d->n_lights, &s.lights)) != IZPI_OK) return rc;
   if ((rc = upload(ctx, d->materials, (size_t)d->n_materials, &s.materials)) != IZPI_OK) return rc;
+  {
+    // u, v of a hit are read by image textures only (Constant / SpectralConstant ignore them: constant.go:21,
+    // spectral_constant.go:65).  A material without image textures lets the shading skip the sphere's atan2 + asin.
+    std::vector<uint8_t> flags((size_t)d->n_materials, 0);
+    auto img = [&](int t) { return t >= 0 && t < d->n_textures && d->textures[t].type == IZPI_TEX_IMAGE; };
+    auto simg = [&](int t) { return t >= 0 && t < d->n_spectral_textures && d->spectral_textures[t].type == IZPI_SPEC_IMAGE; };
+    for (int i = 0; i < d->n_materials; i++) {
+      const izpi_material_spec& m = d->materials[i];
+      if (img(m.tex) || img(m.normal_tex) || img(m.roughness_tex) || img(m.metalness_tex) || simg(m.spectral_tex) || simg(m.spectral_absorption_tex))
+        flags[i] |= kMatNeedsUV;
+    }
+    if ((rc = upload(ctx, flags.data(), flags.size(), &s.mat_flags)) != IZPI_OK) return rc;
+    IZ_CUDA(cudaStreamSynchronize(ctx->stream));  // `flags` is a local
+  }
   // textures: pixel arrays first, then the table that points at them
   std::vector<DTexture>& tex = ctx->h_textures;
   tex.assign((size_t)d->n_textures, DTexture{});
@@ -382,6 +397,9 @@ static int upload_one(izpi_ctx* ctx, const izpi_scene_desc* d) {
     std::memset(&o, 0, sizeof(o));
     o.type = t.type; o.n = t.n; o.peak = t.peak; o.centre = t.centre; o.width = t.width;
     if (t.type == IZPI_SPEC_TABULATED) {
+      if (t.n < 0 || (t.n > 0 && (!t.wavelengths || !t.values))) { set_error("izpi_scene_upload: tabulated spectral texture without samples"); return IZPI_EINVAL; }
+      o.sorted = 1;
+      for (int k = 0; k + 1 < t.n; k++) if (!(t.wavelengths[k] < t.wavelengths[k + 1])) o.sorted = 0;
       if ((rc = upload(ctx, t.wavelengths, (size_t)t.n, &o.wavelengths)) != IZPI_OK) return rc;
       if ((rc = upload(ctx, t.values, (size_t)t.n, &o.values)) != IZPI_OK) return rc;
     }
@@ -467,7 +485,7 @@ int izpi_scene_image_commit(izpi_ctx* dst) {
   DScene& s = dst->scene;
   bool ok = rebase(s.nodes, src, loc) && rebase(s.nodes_t, src, loc) && rebase(s.prims, src, loc) && rebase(s.attrs, src, loc) &&
             rebase(s.xforms, src, loc) && rebase(s.lights, src, loc) && rebase(s.materials, src, loc) && rebase(s.textures, src, loc) &&
-            rebase(s.spectex, src, loc);
+            rebase(s.spectex, src, loc) && rebase(s.mat_flags, src, loc);
   for (DTexture& t : dst->h_textures) ok = ok && rebase(t.pixels, src, loc);
   for (DSpectralTexture& t : dst->h_spectex) ok = ok && rebase(t.wavelengths, src, loc) && rebase(t.values, src, loc);
   if (!ok) { set_error("izpi_scene_image_commit: the image's pointer tables do not match its blocks"); return IZPI_EINVAL; }

@@ -22,6 +22,7 @@ struct DTexture {  // texture.Constant / texture.ImageTxt
 };
 struct DSpectralTexture {  // texture.SpectralConstant
   int32_t type, n;
+  int32_t sorted, pad;  // TABULATED: wavelengths strictly increasing -> the bracketing pair is found by bisection (same pair as the reference's scan)
   double peak, centre, width;
   const double* wavelengths;  // device
   const double* values;       // device
@@ -34,6 +35,9 @@ struct DScene {
   int32_t g4_need;              // most stack entries a ray can need in THIS tree (<= 64, bvh4.go:71); picks the slab size of the 2-lane kernel
   int32_t class_mask;           // bit c set <=> some primitive carries a material of class c (IZPI_MAT_*): shade launches of absent classes are skipped
   int32_t n_textures, n_spectex;
+  int32_t scalar_need;          // stack entries the thread-per-ray traversal can need in this tree (<= 64): sizes its shared-memory stack
+  int32_t pad0;
+  const uint8_t* mat_flags;     // per material: kMatNeedsUV when any of its textures is an image (else sphere UVs -- atan2 + asin -- are never read)
   const float4* nodes;          // 8 x float4 per BVH4Node, verbatim SoA layout, 128-B aligned
   const float4* nodes_t;        // child-major copy: 4 x {minx miny minz maxx | maxy maxz ref cnt}, leaf-nodes folded in, empty slots NaN (context.cu)
   const izpi_prim_rec* prims;   // 80-B records in world order, 16-B aligned
@@ -45,6 +49,8 @@ struct DScene {
   const DSpectralTexture* spectex;
   izpi_camera camera;
 };
+
+constexpr uint8_t kMatNeedsUV = 1;
 
 #define IZ_CUDA(call)                                                                         \
   do {                                                                                        \
@@ -69,7 +75,8 @@ struct SceneBlock {
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor results, per CONTEXT (= per device): 0 = not asked yet
 struct OccupancyCache {
   int trace_g2[2] = {0, 0}, trace_g4 = 0, trace_scalar = 0;
-  int ext = 0, ext4 = 0, ext2[2] = {0, 0}, small = 0;
+  int ext = 0, ext4 = 0, ext2[2] = {0, 0};
+  size_t ext_smem = 0;  // shared memory per block the `ext` figure was asked for (depends on the uploaded tree)
 };
 }  // namespace izpi
 

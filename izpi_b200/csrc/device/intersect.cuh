@@ -125,9 +125,10 @@ __device__ __forceinline__ int tag_xform(uint32_t tag) { return (int)(tag >> 18)
 
 // Primitive.Hit for the record `idx`.  FULL also fills the HitRecord (u, v, p, normal) the way
 // the reference's wrappers compose it.
+// need_uv = false skips the sphere's (u, v) = atan2 / asin (sphere.go:29-35) when the caller never reads them; u = v = 0 then.
 template <bool FULL>
 __device__ __forceinline__ bool prim_hit(const DScene& sc, int idx, const PrimRec& pr, const DRay& ray, double tmin,
-                                         double tmax, DHit& h) {
+                                         double tmax, DHit& h, bool need_uv = true) {
   DRay r = ray;
   const izpi_xform* xf = nullptr;
   int xi = tag_xform(pr.tag);
@@ -176,7 +177,7 @@ __device__ __forceinline__ bool prim_hit(const DScene& sc, int idx, const PrimRe
         d3 on = (point_at(r, t) - c) / pr.a[3];
         d3 outward = on;
         if (dot(r.d, on) >= 0) on = on * -1.0;
-        sphere_uv(on, u, v);
+        if (need_uv) sphere_uv(on, u, v);
         n = root == 1 ? on : outward;  // second root keeps the unflipped normal (sphere.go:88-91)
       }
       break;

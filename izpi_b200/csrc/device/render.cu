@@ -393,7 +393,7 @@ __device__ __noinline__ double path_length(const DScene& sc, d3 hit_p, d3 sdir, 
   if (rec < 0) return 10.0;
   PrimRec pr = load_rec(sc.prims + rec);
   DHit eh;
-  prim_hit<true>(sc, rec, pr, tr, 0.0, DBL_MAX, eh);
+  prim_hit<true>(sc, rec, pr, tr, 0.0, DBL_MAX, eh, false);  // only the exit point is read
   double pl = len(eh.p - hit_p);
   if (pl < 0.1) pl = 0.1;
   if (pl > 100.0) pl = 100.0;
@@ -498,7 +498,7 @@ shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* path
       PrimRec pr = load_rec(sc.prims + p.hit_rec);
       const izpi_material_spec& m = sc.materials[tag_material(pr.tag)];
       DHit h;
-      prim_hit<true>(sc, p.hit_rec, pr, r, 0.001, DBL_MAX, h);
+      prim_hit<true>(sc, p.hit_rec, pr, r, 0.001, DBL_MAX, h, (sc.mat_flags[tag_material(pr.tag)] & kMatNeedsUV) != 0);
       h.t = p.hit_t;
       if (rp.sampler >= IZPI_SAMPLER_ALBEDO) {  // debug AOVs: one hit, no bounce (sampler/albedo.go:30-36, normal.go:28-34)
         d3 aov;
@@ -797,20 +797,24 @@ struct LaunchCfg {
 };
 
 int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
-  lc.smem = (size_t)kStackDepth * kThreads * sizeof(int32_t);
+  // thread-per-ray stage: one int32 stack per thread, as deep as THIS tree can need (a 22-primitive scene needs 4 entries, not
+  // the reference's 64: 2 KB of shared memory per block instead of 32 KB, so occupancy is set by registers alone)
+  const int depth = ctx->scene.world_kind == IZPI_WORLD_BVH4 ? std::min(kStackDepth, std::max(1, ctx->scene.scalar_need + 1)) : 1;
+  lc.smem = (size_t)depth * kThreads * sizeof(int32_t);
   lc.smem4 = (size_t)(kThreads / 4) * kG4Slab * sizeof(int2);
   lc.g2_deep = ctx->scene.g4_need > kG2Stack;  // the 52-entry slab (intersect_g2.cuh)
   const size_t smem2_a = (size_t)(kExt2Threads / 2) * G2Slab<kG2Stack>::kSlots * sizeof(int2);
   const size_t smem2_b = (size_t)(kExt2Threads / 2) * G2Slab<kG2StackDeep>::kSlots * sizeof(int2);
   lc.smem2 = lc.g2_deep ? smem2_b : smem2_a;
   OccupancyCache& oc = ctx->occ;  // per context: function attributes and occupancy belong to a device
-  if (!oc.ext) {
+  if (!oc.ext || oc.ext_smem != lc.smem) {
+    oc.ext_smem = lc.smem;
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.ext2[0], extend_g2_kernel<kG2Stack, false>, kExt2Threads, smem2_a));
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.ext2[1], extend_g2_kernel<kG2StackDeep, false>, kExt2Threads, smem2_b));
     if (oc.ext2[0] < 1) oc.ext2[0] = 1;
     if (oc.ext2[1] < 1) oc.ext2[1] = 1;
-    IZ_CUDA(cudaFuncSetAttribute(extend_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
-    IZ_CUDA(cudaFuncSetAttribute(extend_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
+    IZ_CUDA(cudaFuncSetAttribute(extend_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kStackDepth * kThreads * sizeof(int32_t))));
+    IZ_CUDA(cudaFuncSetAttribute(extend_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kStackDepth * kThreads * sizeof(int32_t))));
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.ext4, extend_g4_kernel<false>, kThreads, lc.smem4));
     if (oc.ext4 < 1) oc.ext4 = 1;
     IZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc.ext, extend_kernel<false>, kThreads, lc.smem));

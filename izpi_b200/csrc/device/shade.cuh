@@ -66,9 +66,7 @@ __device__ __forceinline__ void sample_wavelength(double random, double& lambda,
 __device__ __forceinline__ d3 cie_values(double wl) {
   if (wl <= 380.0) return mk(c_cie[0][0], c_cie[1][0], c_cie[2][0]);
   if (wl >= 750.0) return mk(c_cie[0][74], c_cie[1][74], c_cie[2][74]);
-  int index = 0;
-  for (int i = 0; i < 75; i++)
-    if (cie_wavelength(i) >= wl) { index = i; break; }
+  int index = cie_bucket_at_or_above(wl);  // first i with cieWavelengths[i] >= wl (spectral.go:235-241); 380 < wl < 750 here, so index >= 1
   double w1 = cie_wavelength(index - 1), w2 = cie_wavelength(index);
   double t = (wl - w1) / (w2 - w1);
   return mk(c_cie[0][index - 1] + t * (c_cie[0][index] - c_cie[0][index - 1]),
@@ -200,7 +198,7 @@ __device__ __forceinline__ double light_pdf_value(const DScene& sc, int rec, d3 
   DRay r;
   r.o = o; r.d = v; r.time = 0; r.lambda = 0;
   DHit h;
-  if (!prim_hit<true>(sc, rec, pr, r, 0.001, DBL_MAX, h)) return 0.0;
+  if (!prim_hit<true>(sc, rec, pr, r, 0.001, DBL_MAX, h, false)) return 0.0;  // PDFValue reads t and the normal, never u, v
   if (type == IZPI_PRIM_SPHERE) {
     double cos_theta_max = sqrt(1 - pr.a[3] * pr.a[3] / sqlen(mk(pr.a[0], pr.a[1], pr.a[2]) - o));
     double solid_angle = 2 * M_PI * (1 - cos_theta_max);
@@ -216,10 +214,40 @@ __device__ __forceinline__ d3 lights_random(const DScene& sc, d3 o, Rng& rng) {
   int index = (int)(rnd(rng) * (double)sc.n_lights);
   return light_random(sc, sc.lights[index], o, rng);
 }
+// HitableSlice.PDFValue (hitable_slice.go:98-105): sum over the lights of weight * PDFValue, in list order.
+// A direction hits few of the lights, and the expensive part of a light's PDFValue (square roots, divisions, the hit record)
+// runs only for those -- under SIMT that tail would execute once per light with the two or three lanes that hit it.  So the
+// loop is split: a cheap, lane-uniform pass marks each lane's CANDIDATE lights (spheres: the discriminant test of
+// sphere.go:68-72, exactly the reference's; rects and triangles: always), then every lane walks its own candidates, so
+// different lanes evaluate different lights in the same iteration.  A light that is not a candidate contributes
+// weight * 0 = +0, which leaves the running sum unchanged, and each lane still adds its terms in list order: same value.
 __device__ __forceinline__ double lights_pdf_value(const DScene& sc, d3 o, d3 v) {
   double weight = 1.0 / (double)sc.n_lights;
   double sum = 0.0;
-  for (int i = 0; i < sc.n_lights; i++) sum += weight * light_pdf_value(sc, sc.lights[i], o, v);
+  const double vv = dot(v, v);
+  for (int base = 0; base < sc.n_lights; base += 32) {
+    const int m = sc.n_lights - base < 32 ? sc.n_lights - base : 32;
+    unsigned cand = 0;
+    for (int k = 0; k < m; k++) {
+      const izpi_prim_rec* p = sc.prims + sc.lights[base + k];
+      const int type = tag_type(__ldg(&p->tag));
+      bool c = type == IZPI_PRIM_XZRECT || type == IZPI_PRIM_TRIANGLE;
+      if (type == IZPI_PRIM_SPHERE) {  // Sphere.Hit's `discriminant > 0` (sphere.go:68-72), same operation order as sphere_test
+        const double2 c01 = __ldg(reinterpret_cast<const double2*>(p->a));
+        const double2 c2r = __ldg(reinterpret_cast<const double2*>(p->a) + 1);
+        d3 oc = o - mk(c01.x, c01.y, c2r.x);
+        double b = dot(oc, v);
+        double cc = dot(oc, oc) - (c2r.y * c2r.y);
+        c = (b * b) - (vv * cc) > 0;
+      }
+      cand |= (c ? 1u : 0u) << k;
+    }
+    while (cand) {
+      const int k = __ffs(cand) - 1;
+      cand &= cand - 1;
+      sum += weight * light_pdf_value(sc, sc.lights[base + k], o, v);
+    }
+  }
   return sum;
 }
 

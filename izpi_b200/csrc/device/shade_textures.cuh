@@ -13,6 +13,17 @@ __device__ __forceinline__ long long go_int(double x) {
   return (long long)x;
 }
 
+// first i in 0..74 with lambda <= 380 + 5 i, for 380 <= lambda <= 750 (the linear scans of spectral_image.go:228-245 and
+// spectral.go:235-241): an estimate from the division, corrected against the exact grid values
+__device__ __forceinline__ int cie_bucket_at_or_above(double lambda) {
+  int i = (int)((lambda - 380.0) / 5.0);
+  if (i < 0) i = 0;
+  if (i > 74) i = 74;
+  while (i < 74 && !(lambda <= 380.0 + 5.0 * (double)i)) i++;
+  while (i > 0 && lambda <= 380.0 + 5.0 * (double)(i - 1)) i--;
+  return i;
+}
+
 __device__ __forceinline__ d3 texture_value(const DScene& sc, int tex, double u, double v) {
   const DTexture& t = sc.textures[tex];
   if (t.type == IZPI_TEX_CONSTANT) return mk(t.color[0], t.color[1], t.color[2]);
@@ -28,11 +39,29 @@ __device__ __forceinline__ d3 texture_value(const DScene& sc, int tex, double u,
   return mk(rg.x, rg.y, b);
 }
 
-__device__ __forceinline__ double spd_interp(const double* w, const double* val, int n, double lambda) {
+// The bracketing pair of `lambda` in a STRICTLY INCREASING table with w[0] <= lambda <= w[n-1]: the smallest i with
+// lambda <= w[i+1].  That is the pair the reference's linear scans stop at (the first i with w[i] <= lambda <= w[i+1]:
+// every earlier pair fails lambda <= w[j+1], and lambda > w[i] for i > 0 because pair i-1 failed), found in log2(n) steps.
+__device__ __forceinline__ int spd_bracket(const double* w, int n, double lambda) {
+  int lo = 0, hi = n - 2;  // answer in [lo, hi]
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (lambda <= __ldg(w + mid + 1)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ double spd_interp(const double* w, const double* val, int n, double lambda, bool sorted) {
   // interpolateSPD (spectral_constant.go:78-106): clamp outside, first bracketing pair inside
   if (n == 0) return 0.0;
   if (lambda < w[0]) return val[0];
   if (lambda > w[n - 1]) return val[n - 1];
+  if (sorted && n >= 2) {
+    int i = spd_bracket(w, n, lambda);
+    double w1 = __ldg(w + i), w2 = __ldg(w + i + 1);
+    double t = (lambda - w1) / (w2 - w1);
+    return __ldg(val + i) + t * (__ldg(val + i + 1) - __ldg(val + i));
+  }
   for (int i = 0; i < n - 1; i++) {
     double w1 = w[i], w2 = w[i + 1];
     if (lambda >= w1 && lambda <= w2) {
@@ -66,13 +95,10 @@ __device__ __forceinline__ double spectral_value(const DScene& sc, int tex, doub
     int idx = 74;
     if (lambda < 380.0) idx = 0;
     else if (lambda > 750.0) idx = 74;
-    else {
-      for (int i = 0; i < 75; i++)
-        if (lambda <= 380.0 + 5.0 * (double)i) { idx = i; break; }
-    }
+    else idx = cie_bucket_at_or_above(lambda);
     return rgb_to_spectral_value(rgb.x, rgb.y, rgb.z, 380.0 + 5.0 * (double)idx);
   }
-  if (t.type == IZPI_SPEC_TABULATED) return spd_interp(t.wavelengths, t.values, t.n, lambda);
+  if (t.type == IZPI_SPEC_TABULATED) return spd_interp(t.wavelengths, t.values, t.n, lambda, t.sorted != 0);
   double e = (lambda - t.centre) / t.width;
   return t.peak * exp(-(e * e));  // math.Pow(x, 2) is exactly x*x
 }
