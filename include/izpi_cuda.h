@@ -262,6 +262,7 @@ int izpi_render_finish(izpi_ctx* ctx, double* canvas_rgba, uint64_t* total_rays)
 typedef struct izpi_render_stats {
   uint64_t rays, nodes_visited, prim_tests;
   uint64_t extend_launches;
+  uint64_t material_bins; /* bins the hits are sorted into between bounces: one per image-textured material + one per class for the rest */
   double extend_ms; /* summed device time of the extend (closest-hit) launches */
   double shade_ms;  /* ... of the shade launches + queue advance */
   double other_ms;  /* ... of ray generation and resolve */

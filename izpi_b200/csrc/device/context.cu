@@ -372,7 +372,34 @@ static int upload_one(izpi_ctx* ctx, const izpi_scene_desc* d) {
         flags[i] |= kMatNeedsUV;
     }
     if ((rc = upload(ctx, flags.data(), flags.size(), &s.mat_flags)) != IZPI_OK) return rc;
-    IZ_CUDA(cudaStreamSynchronize(ctx->stream));  // `flags` is a local
+    // material -> bin (dscene.cuh): per class one shared bin for the materials without image textures, then one bin per
+    // image-textured material while bins last (kMaxBins); the overflow shares the class's textured bins round-robin.
+    // IZPI_MATERIAL_BINS=0 files everything under its class bin (the round-1 behaviour; for A/B measurements).
+    const char* env = getenv("IZPI_MATERIAL_BINS");
+    const bool by_material = !(env && env[0] == '0');
+    std::vector<uint8_t> bin((size_t)d->n_materials, 0);
+    int base[5] = {-1, -1, -1, -1, -1};   // first bin of a class: its plain materials, or its first textured one when it has no plain ones
+    bool has_plain[5] = {false, false, false, false, false}, base_taken[5] = {false, false, false, false, false};
+    std::vector<int> pool[5];             // bins holding textured materials of a class
+    s.n_bins = 0;
+    for (int i = 0; i < d->n_materials; i++) {
+      const int cls = d->materials[i].type;
+      if (cls < 0 || cls > IZPI_MAT_PBR) { set_error("izpi_scene_upload: unknown material type"); return IZPI_EINVAL; }
+      if (!(flags[i] & kMatNeedsUV) || !by_material) has_plain[cls] = true;
+    }
+    for (int c = 0; c < 5; c++)
+      if ((s.class_mask >> c) & 1) { s.bin_class[s.n_bins] = (uint8_t)c; base[c] = s.n_bins++; }
+    size_t rr = 0;
+    for (int i = 0; i < d->n_materials; i++) {
+      const int cls = d->materials[i].type;
+      if (base[cls] < 0) continue;  // no primitive carries this class: never binned
+      if (!(flags[i] & kMatNeedsUV) || !by_material) { bin[i] = (uint8_t)base[cls]; continue; }
+      if (!has_plain[cls] && !base_taken[cls]) { base_taken[cls] = true; pool[cls].push_back(base[cls]); bin[i] = (uint8_t)base[cls]; continue; }
+      if (s.n_bins < kMaxBins) { s.bin_class[s.n_bins] = (uint8_t)cls; pool[cls].push_back(s.n_bins); bin[i] = (uint8_t)s.n_bins++; continue; }
+      bin[i] = (uint8_t)(pool[cls].empty() ? base[cls] : pool[cls][rr++ % pool[cls].size()]);  // out of bins: share
+    }
+    if ((rc = upload(ctx, bin.data(), bin.size(), &s.mat_bin)) != IZPI_OK) return rc;
+    IZ_CUDA(cudaStreamSynchronize(ctx->stream));  // `flags`, `bin` are locals
   }
   // textures: pixel arrays first, then the table that points at them
   std::vector<DTexture>& tex = ctx->h_textures;
@@ -485,7 +512,7 @@ int izpi_scene_image_commit(izpi_ctx* dst) {
   DScene& s = dst->scene;
   bool ok = rebase(s.nodes, src, loc) && rebase(s.nodes_t, src, loc) && rebase(s.prims, src, loc) && rebase(s.attrs, src, loc) &&
             rebase(s.xforms, src, loc) && rebase(s.lights, src, loc) && rebase(s.materials, src, loc) && rebase(s.textures, src, loc) &&
-            rebase(s.spectex, src, loc) && rebase(s.mat_flags, src, loc);
+            rebase(s.spectex, src, loc) && rebase(s.mat_flags, src, loc) && rebase(s.mat_bin, src, loc);
   for (DTexture& t : dst->h_textures) ok = ok && rebase(t.pixels, src, loc);
   for (DSpectralTexture& t : dst->h_spectex) ok = ok && rebase(t.wavelengths, src, loc) && rebase(t.values, src, loc);
   if (!ok) { set_error("izpi_scene_image_commit: the image's pointer tables do not match its blocks"); return IZPI_EINVAL; }

@@ -37,6 +37,12 @@ struct DScene {
   int32_t n_textures, n_spectex;
   int32_t scalar_need;          // stack entries the thread-per-ray traversal can need in this tree (<= 64): sizes its shared-memory stack
   int32_t pad0;
+  // Material bins of the wavefront renderer (north_star 3: paths sorted by material ID between bounces).  A hit is filed
+  // under mat_bin[material]; a bin holds ONE class (IZPI_MAT_*), every material with image textures has a bin of its own
+  // (a warp of the shade kernel then samples one texture set), materials without image textures share their class's bin.
+  int32_t n_bins;
+  uint8_t bin_class[32];
+  const uint8_t* mat_bin;
   const uint8_t* mat_flags;     // per material: kMatNeedsUV when any of its textures is an image (else sphere UVs -- atan2 + asin -- are never read)
   const float4* nodes;          // 8 x float4 per BVH4Node, verbatim SoA layout, 128-B aligned
   const float4* nodes_t;        // child-major copy: 4 x {minx miny minz maxx | maxy maxz ref cnt}, leaf-nodes folded in, empty slots NaN (context.cu)
@@ -51,6 +57,7 @@ struct DScene {
 };
 
 constexpr uint8_t kMatNeedsUV = 1;
+constexpr int kMaxBins = 32;
 
 #define IZ_CUDA(call)                                                                         \
   do {                                                                                        \

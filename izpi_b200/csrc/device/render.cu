@@ -4,9 +4,10 @@
 // One path = one (pixel, sample).  A batch of paths lives in HBM as 160-byte PathState records;
 // each bounce runs
 //   extend_kernel   closest hit for every live path (persistent warps, the trace kernel's traversal),
-//                   misses terminate, hits are binned BY MATERIAL CLASS with warp match/ballot/popc
-//                   prefix ranks and one atomicAdd per (warp, class);
-//   shade_kernel<C> one launch per class over its bin: emission, BSDF sampling, light/BSDF mixture PDF
+//                   misses terminate, hits are filed BY MATERIAL (dscene.cuh: one bin per image-textured material, one
+//                   shared bin per class for the rest) with warp match/ballot/popc prefix ranks and one
+//                   atomicAdd per (warp, bin): a counting sort by material ID into per-material bins;
+//   shade_kernel<C> one launch per class over its bins, material after material: emission, BSDF sampling, light/BSDF mixture PDF
 //                   (sampler/colour.go:33-65, sampler/spectral.go:47-80 in iterative form), survivors
 //                   are compacted into the next bounce's queue the same way;
 // then resolve_kernel sums each pixel's samples in sample order (the reference's loop order,
@@ -26,6 +27,7 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kStackDepth = 64;
 constexpr int kClasses = 5;  // IZPI_MAT_* types
+constexpr int kBinCounters = 16;  // first bin counter; kBinCounters + kMaxBins counters per queue set
 
 struct alignas(16) PathState {
   double ox, oy, oz, dx, dy, dz, time, lambda;  // ray.RayImpl
@@ -53,8 +55,8 @@ struct RenderParams {
 struct Queues {
   int32_t* cur;                 // live paths entering this bounce
   int32_t* next;                // survivors
-  int32_t* bins;                // [kClasses][capacity]
-  unsigned long long* counters; // [0] cur count, [1] next count, [2..6] bin counts, [7] work head, [8] rays traced, [9] nodes visited, [10] primitive tests (counting kernels)
+  int32_t* bins;                // [n_bins][capacity]
+  unsigned long long* counters; // [0] cur count, [1] next count, [7] work head, [8] rays traced, [9] nodes visited, [10] primitive tests (counting kernels), [kBinCounters + b] count of bin b
   int32_t capacity;
 };
 
@@ -198,12 +200,12 @@ extend_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* pat
         } else {
           p.hit_rec = rec; p.hit_t = t;
           hit = true;
-          cls = sc.materials[tag_material(sc.prims[rec].tag)].type;
+          cls = sc.mat_bin[tag_material(sc.prims[rec].tag)];
         }
       }
     }
     __syncwarp();
-    push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + 2);
+    push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + kBinCounters);
   }
   if (traced) atomicAdd(&q.counters[8], traced);
   if (COUNT) { atomicAdd(&q.counters[9], (unsigned long long)nn); atomicAdd(&q.counters[10], (unsigned long long)np); }
@@ -276,10 +278,10 @@ extend_g4_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
         } else {
           p.hit_rec = s.best; p.hit_t = s.tmax;
           hit = true;
-          cls = sc.materials[tag_material(sc.prims[s.best].tag)].type;
+          cls = sc.mat_bin[tag_material(sc.prims[s.best].tag)];
         }
       }
-      push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + 2);
+      push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + kBinCounters);
       if (done) pi = -1;
     }
   }
@@ -366,10 +368,10 @@ extend_g2_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* 
         } else {
           p.hit_rec = s.best; p.hit_t = s.tmax;
           hit = true;
-          cls = sc.materials[tag_material(sc.prims[s.best].tag)].type;
+          cls = sc.mat_bin[tag_material(sc.prims[s.best].tag)];
         }
       }
-      push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + 2);
+      push_binned(hit, cls, pi, q.bins, q.capacity, q.counters + kBinCounters);
       if (done) pi = -1;
     }
   }
@@ -484,15 +486,35 @@ template <int CLS>
 #endif
 __global__ void __launch_bounds__(kThreads, (CLS == IZPI_MAT_DIELECTRIC ? IZPI_SHADE_MIN_BLOCKS_DIELECTRIC : IZPI_SHADE_MIN_BLOCKS))
 shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* paths, Queues q) {
-  const long long n = (long long)q.counters[2 + CLS];
-  const int32_t* bin = q.bins + (size_t)CLS * q.capacity;
+  // The bins of this class, one after the other: each bin's range is padded to whole warps, so a warp shades ONE material's
+  // paths (one texture set) and stays in the loop for the ballots.
+  __shared__ long long s_begin[kMaxBins + 1];
+  __shared__ int s_bin[kMaxBins];
+  __shared__ int s_nb;
+  if (threadIdx.x == 0) {
+    int nb = 0;
+    long long at = 0;
+    for (int b = 0; b < sc.n_bins; b++) {
+      if (sc.bin_class[b] != CLS) continue;
+      s_bin[nb] = b; s_begin[nb] = at;
+      at += ((long long)q.counters[kBinCounters + b] + 31) & ~31ll;
+      nb++;
+    }
+    s_begin[nb] = at; s_nb = nb;
+  }
+  __syncthreads();
+  const int nb = s_nb;
+  const long long n_round = s_begin[nb];
   const bool spectral = rp.sampler == IZPI_SAMPLER_SPECTRAL;
-  const long long n_round = (n + 31) & ~31ll;  // whole warps stay in the loop for the ballots
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_round; i += (long long)gridDim.x * blockDim.x) {
     bool survive = false;
     int32_t pi = -1;
-    if (i < n) {
-      pi = bin[i];
+    int k = 0;
+    while (k + 1 < nb && i >= s_begin[k + 1]) k++;
+    const int b = s_bin[k];
+    const long long li = i - s_begin[k];
+    if (li < (long long)q.counters[kBinCounters + b]) {
+      pi = q.bins[(size_t)b * q.capacity + li];
       PathState& p = paths[pi];
       DRay r = path_ray(p);
       PrimRec pr = load_rec(sc.prims + p.hit_rec);
@@ -599,7 +621,7 @@ __global__ void advance_kernel(Queues q, unsigned long long* host_visible_count)
   q.counters[0] = q.counters[1];
   *host_visible_count = q.counters[1];
   q.counters[1] = 0;
-  for (int c = 0; c < kClasses; c++) q.counters[2 + c] = 0;
+  for (int b = 0; b < kMaxBins; b++) q.counters[kBinCounters + b] = 0;
   q.counters[7] = 0;
 }
 
@@ -741,6 +763,7 @@ struct RenderState {
   BatchSlot slot[kSlots];
   int32_t batch_paths = 1 << 24;  // paths per batch: 16M x 160 B = 2.7 GB of HBM per slot
   bool allocated = false;
+  int bins_allocated = 0;
   std::vector<TileRun> rendered;  // what izpi_render_finish of a device group has to move
   long long rendered_pixels = 0;
   // IZPI_RENDER_STATS: per-stage CUDA-event time (batches serialised) and counting extend kernels
@@ -858,7 +881,7 @@ int batch_start(izpi_ctx* ctx, RenderState* r, BatchSlot& s, int batch, const ui
     s.pixel_capacity = n_pixels;
   }
   IZ_CUDA(cudaMemcpyAsync(s.d_pixels, px, (size_t)n_pixels * 4, cudaMemcpyHostToDevice, st));
-  IZ_CUDA(cudaMemsetAsync(s.q.counters, 0, 11 * sizeof(unsigned long long), st));
+  IZ_CUDA(cudaMemsetAsync(s.q.counters, 0, (kBinCounters + kMaxBins) * sizeof(unsigned long long), st));
   long long n = (long long)n_pixels * s_count;
   int gen_grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
   int rc = span_begin(r, st, 2);
@@ -1029,8 +1052,7 @@ int setup_one(izpi_ctx* ctx, const izpi_render_config* cfg) {
       IZ_CUDA(cudaMalloc(&s.d_paths, (size_t)cap * sizeof(PathState)));
       IZ_CUDA(cudaMalloc(&s.q.cur, (size_t)cap * 4));
       IZ_CUDA(cudaMalloc(&s.q.next, (size_t)cap * 4));
-      IZ_CUDA(cudaMalloc(&s.q.bins, (size_t)cap * 4 * kClasses));
-      IZ_CUDA(cudaMalloc(&s.q.counters, 16 * sizeof(unsigned long long)));
+      IZ_CUDA(cudaMalloc(&s.q.counters, (kBinCounters + kMaxBins) * sizeof(unsigned long long)));
       s.q.capacity = cap;
       IZ_CUDA(cudaHostAlloc(&s.h_count, 8 * sizeof(unsigned long long), cudaHostAllocMapped));
       IZ_CUDA(cudaHostGetDevicePointer(&s.d_count_mapped, s.h_count, 0));
@@ -1042,6 +1064,13 @@ int setup_one(izpi_ctx* ctx, const izpi_render_config* cfg) {
   }
   rc = sync_slots(r);
   if (rc != IZPI_OK) return rc;
+  if (ctx->scene.n_bins > r->bins_allocated) {  // one bin per image-textured material: the count belongs to the uploaded scene
+    for (BatchSlot& s : r->slot) {
+      cudaFree(s.q.bins); s.q.bins = nullptr;
+      IZ_CUDA(cudaMalloc(&s.q.bins, (size_t)s.q.capacity * 4 * (size_t)ctx->scene.n_bins));
+    }
+    r->bins_allocated = ctx->scene.n_bins;
+  }
   IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px_hidden * 32, ctx->stream));
   IZ_CUDA(cudaMemsetAsync(r->d_total_rays, 0, 4 * sizeof(unsigned long long), ctx->stream));
   IZ_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1244,6 +1273,7 @@ int izpi_render_get_stats(izpi_ctx* ctx, izpi_render_stats* out) {
   if (!ctx || !out) { set_error("izpi_render_get_stats: bad argument"); return IZPI_EINVAL; }
   if (!ctx->render) { set_error("izpi_render_get_stats: izpi_render_setup has not been called"); return IZPI_ESTATE; }
   std::memset(out, 0, sizeof(*out));
+  out->material_bins = (uint64_t)ctx->scene.n_bins;
   std::vector<izpi_ctx*> members{ctx};
   members.insert(members.end(), ctx->subs.begin(), ctx->subs.end());
   for (izpi_ctx* m : members) {

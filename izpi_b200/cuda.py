@@ -39,7 +39,7 @@ class RenderConfig(C.Structure):
 
 
 class RenderStats(C.Structure):
-    _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("extend_launches", C.c_uint64),
+    _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("extend_launches", C.c_uint64), ("material_bins", C.c_uint64),
                 ("extend_ms", C.c_double), ("shade_ms", C.c_double), ("other_ms", C.c_double)]
 
 

@@ -292,19 +292,29 @@ _CORNELL_RGB = {"White": (0.73, 0.73, 0.73), "Green": (0, 0.73, 0), "Red": (0.73
 
 
 def cornell_pbr_mesh(aspect: float = 1.0, n_around: int = 1000, n_tube: int = 500, tex_size: int = 2048,
-                     bvh_seed: int = 12345) -> SceneSpec:
+                     bvh_seed: int = 12345, n_pbr_materials: int = 1) -> SceneSpec:
     """Config 3: RGB Cornell walls (12 triangles above, materials of scenes.CornellBoxRGB
-    scenes.go:934-1378) + the config-2 torus scaled x0.55 into the box, PBR with image textures."""
+    scenes.go:934-1378) + the config-2 torus scaled x0.55 into the box, PBR with image textures.
+    n_pbr_materials > 1 (not a BASELINE config) splits the mesh into bands around the torus, each with its own PBR material and
+    its own four textures: the multi-material case that sorting hits by material ID is for."""
     sc = SceneSpec(world_kind=S.WORLD_BVH4, bvh_seed=bvh_seed)
     mats = {k: sc.lambertian(sc.constant_texture(f32(v))) for k, v in _CORNELL_RGB.items()}
     mats["white_light"] = sc.diffuse_light(sc.constant_texture(f32((15, 15, 15))))
     alb, rough, metal, nrm = pbr_textures(tex_size)
-    pbr = sc.pbr(sc.image_texture(alb), sc.image_texture(nrm), sc.image_texture(rough), sc.image_texture(metal))
+    pbrs = []
+    for k in range(max(1, n_pbr_materials)):
+        a = alb if k == 0 else np.ascontiguousarray(np.roll(alb, 97 * k, axis=1)[..., [(0 + k) % 3, (1 + k) % 3, (2 + k) % 3, 3]])
+        r, m, n_ = (rough, metal, nrm) if k == 0 else (np.roll(rough, 31 * k, axis=0).copy(), np.roll(metal, 53 * k, axis=1).copy(), nrm.copy())
+        pbrs.append(sc.pbr(sc.image_texture(a), sc.image_texture(n_), sc.image_texture(r), sc.image_texture(m)))
     verts = f32(np.array([[t[0], t[1], t[2]] for t in _PYRAMID_TRIS], dtype=np.float64))
     uvs = np.zeros((len(_PYRAMID_TRIS), 3, 2))
     uvs[0] = [(0, 0), (1, 0), (1, 1)]
     sc.triangles(verts, np.array([mats[t[3]] for t in _PYRAMID_TRIS], dtype=np.int32), uvs)
     tv, tuv = torus_mesh(n_around, n_tube, centre=(50.0, 40.0, 50.0), major=30.0, minor=12.0, amp=3.0, scale=0.55)
-    sc.triangles(tv, pbr, tuv)
+    if len(pbrs) == 1:
+        sc.triangles(tv, pbrs[0], tuv)
+    else:  # bands of 8 quads around the torus, materials in rotation
+        quad_row = np.arange(len(tv)) // (2 * n_tube)
+        sc.triangles(tv, np.asarray(pbrs, dtype=np.int32)[(quad_row // 8) % len(pbrs)], tuv)
     sc.set_camera(f32((50, 50, -140)), f32((50, 50, 0)), f32((0, 1, 0)), f32(40), aspect, f32(0), f32(10), f32(0), f32(1), f32(1.0))
     return sc

@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     from izpi_b200 import scene as S
     assert S.PRIM_DTYPE.itemsize == 168 and S.NODE_DTYPE.itemsize == 128
     assert C.sizeof(S.MaterialSpec) == 64 and C.sizeof(S.TextureSpec) == 48 and C.sizeof(S.CameraSpec) == 128
-    assert C.sizeof(cuda.RenderConfig) == 88 and C.sizeof(cuda.TraceStats) == 32 and C.sizeof(cuda.RenderStats) == 56
+    assert C.sizeof(cuda.RenderConfig) == 88 and C.sizeof(cuda.TraceStats) == 32 and C.sizeof(cuda.RenderStats) == 64
     from izpi_b200 import proto
     # sizeof() of the same structs compiled from include/izpi_proto.h / izpi_scene.h with gcc
     assert C.sizeof(proto.ProtoOptions) == 72 and C.sizeof(proto.ProtoImage) == 24 and C.sizeof(proto.ProtoSPD) == 32
@@ -55,7 +55,7 @@ def test_headers_compile_as_plain_c(tmp_path):
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)], text=True).split()
-    assert [int(x) for x in out] == [56, 72, 200, 80, 176, 128, 88, 168, 64]
+    assert [int(x) for x in out] == [64, 72, 200, 80, 176, 128, 88, 168, 64]
 
 
 def _has_gpu():

@@ -86,6 +86,25 @@ def test_pbr_mesh_same_path(ctx, oracle_mod):
     _same_path(ctx, oracle_mod, sc, 40, 40, 8, cuda.SAMPLER_COLOUR)
 
 
+def test_many_pbr_materials_sorted_by_material(ctx, oracle_mod):
+    """Six PBR materials with their own image textures: hits are filed in one bin per material between bounces (north_star 3:
+    sort by material ID); same paths, same pixels as the oracle, and as with the class-only bins."""
+    sc = scenes.cornell_pbr_mesh(1.0, n_around=96, n_tube=40, tex_size=64, n_pbr_materials=6)
+    img, _ = _same_path(ctx, oracle_mod, sc, 48, 48, 8, cuda.SAMPLER_COLOUR)
+    r = render.New(ctx, 48, 48, 8, 50, sampler_type=cuda.SAMPLER_COLOUR, seed=5)
+    r.Render()
+    assert ctx.render_stats()["material_bins"] == 2 + 6  # Lambert + DiffuseLight share per class, one bin per textured PBR material
+    os.environ["IZPI_MATERIAL_BINS"] = "0"
+    try:
+        ctx.upload(cuda.HostScene(sc))
+        flat, _ = ctx.render(48, 48, 8, sampler=cuda.SAMPLER_COLOUR, seed=5)
+        render.New(ctx, 48, 48, 1, 50, seed=5).Render()
+        assert ctx.render_stats()["material_bins"] == 3
+    finally:
+        del os.environ["IZPI_MATERIAL_BINS"]
+    assert flat.tobytes() == img.tobytes()
+
+
 def test_metal_and_coloured_glass_same_path(ctx, oracle_mod):
     sc = scenes.cornell_box(1.0)
     sc.world_kind = S.WORLD_BVH4  # SetWorld happens on the transport path only (transport.go:83-89)
