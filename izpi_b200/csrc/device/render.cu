@@ -761,7 +761,7 @@ struct RenderState {
   double* d_bg = nullptr;
   unsigned long long* d_total_rays = nullptr;  // [0] rays traced, [1] nodes visited, [2] primitive tests (counting kernels)
   BatchSlot slot[kSlots];
-  int32_t batch_paths = 1 << 24;  // paths per batch: 16M x 160 B = 2.7 GB of HBM per slot
+  int64_t batch_paths_env = 0;  // IZPI_BATCH_PATHS: paths per batch (default: chosen per scene in setup_one)
   bool allocated = false;
   int bins_allocated = 0;
   std::vector<TileRun> rendered;  // what izpi_render_finish of a device group has to move
@@ -845,7 +845,9 @@ int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
   }
   lc.ext_blocks = oc.ext; lc.ext4_blocks = oc.ext4; lc.ext2_blocks = oc.ext2[lc.g2_deep ? 1 : 0];
   // tiny trees (config 4 has 22 primitives) stay cache-resident and coherent: the thread-per-ray stage wins there
-  lc.use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= 64;
+  int coop_min_nodes = 64;
+  if (const char* e = getenv("IZPI_COOP_MIN_NODES")) coop_min_nodes = atoi(e);
+  lc.use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= coop_min_nodes;
   lc.use_g2 = lc.use_g4 && ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2StackDeep;
   lc.count = ctx->render && ctx->render->count_on;
   return IZPI_OK;
@@ -1016,7 +1018,7 @@ int setup_one(izpi_ctx* ctx, const izpi_render_config* cfg) {
     r = new RenderState();
     ctx->render = r;
     const char* e = getenv("IZPI_BATCH_PATHS");
-    if (e) { long v = atol(e); if (v >= 1024 && v <= (1l << 28)) r->batch_paths = (int32_t)v; }
+    if (e) { long v = atol(e); if (v >= 1024 && v <= (1l << 28)) r->batch_paths_env = v; }
   }
   r->cfg = *cfg;
   r->stats_on = (cfg->flags & (IZPI_RENDER_STATS | IZPI_RENDER_TIMING)) != 0;
@@ -1047,13 +1049,8 @@ int setup_one(izpi_ctx* ctx, const izpi_render_config* cfg) {
   }
   if (!r->allocated) {
     IZ_CUDA(cudaMalloc(&r->d_total_rays, 4 * sizeof(unsigned long long)));
-    int32_t cap = r->batch_paths;
     for (BatchSlot& s : r->slot) {
-      IZ_CUDA(cudaMalloc(&s.d_paths, (size_t)cap * sizeof(PathState)));
-      IZ_CUDA(cudaMalloc(&s.q.cur, (size_t)cap * 4));
-      IZ_CUDA(cudaMalloc(&s.q.next, (size_t)cap * 4));
       IZ_CUDA(cudaMalloc(&s.q.counters, (kBinCounters + kMaxBins) * sizeof(unsigned long long)));
-      s.q.capacity = cap;
       IZ_CUDA(cudaHostAlloc(&s.h_count, 8 * sizeof(unsigned long long), cudaHostAllocMapped));
       IZ_CUDA(cudaHostGetDevicePointer(&s.d_count_mapped, s.h_count, 0));
       IZ_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -1064,12 +1061,32 @@ int setup_one(izpi_ctx* ctx, const izpi_render_config* cfg) {
   }
   rc = sync_slots(r);
   if (rc != IZPI_OK) return rc;
-  if (ctx->scene.n_bins > r->bins_allocated) {  // one bin per image-textured material: the count belongs to the uploaded scene
+  // Paths per batch.  Every batch ends in ~50 nearly empty bounces (the few paths caught between glass and metal), whose cost
+  // is latency, not work: the fewer batches a frame has, the smaller their share.  Large trees, where one bounce of a full
+  // batch takes tens of milliseconds, gain 6-12 % from 64 M paths per batch over 16 M (config 3: 214 -> 241 Msamples/s, config 5:
+  // 169 -> 189, profiles/r02_tune_batch.log); the tiny scenes of the thread-per-ray stage do not (config 4: -1.5 %).  The
+  // buffers are sized for the frame at hand (160 B of path state + queues per path: 11.6 GB per slot at 64 M) and only grow.
+  LaunchCfg lc0;
+  if ((rc = launch_cfg(ctx, lc0)) != IZPI_OK) return rc;
+  int64_t want_cap = r->batch_paths_env ? r->batch_paths_env : (lc0.use_g4 ? (int64_t)1 << 26 : (int64_t)1 << 24);
+  const int64_t frame_paths = (int64_t)n_px * (int64_t)std::max(1, cfg->sample_count);
+  if (frame_paths < want_cap) want_cap = std::max<int64_t>(frame_paths, 1 << 16);
+  if (want_cap > r->slot[0].q.capacity || ctx->scene.n_bins > r->bins_allocated) {
+    const int32_t cap = (int32_t)std::max<int64_t>(want_cap, r->slot[0].q.capacity);
     for (BatchSlot& s : r->slot) {
+      if (cap > s.q.capacity) {
+        cudaFree(s.d_paths); cudaFree(s.q.cur); cudaFree(s.q.next);
+        s.d_paths = nullptr; s.q.cur = s.q.next = nullptr; s.q.capacity = 0;
+        IZ_CUDA(cudaMalloc(&s.d_paths, (size_t)cap * sizeof(PathState)));
+        IZ_CUDA(cudaMalloc(&s.q.cur, (size_t)cap * 4));
+        IZ_CUDA(cudaMalloc(&s.q.next, (size_t)cap * 4));
+        s.q.capacity = cap;
+      }
+      // one bin per image-textured material: the count belongs to the uploaded scene
       cudaFree(s.q.bins); s.q.bins = nullptr;
-      IZ_CUDA(cudaMalloc(&s.q.bins, (size_t)s.q.capacity * 4 * (size_t)ctx->scene.n_bins));
+      IZ_CUDA(cudaMalloc(&s.q.bins, (size_t)s.q.capacity * 4 * (size_t)std::max(ctx->scene.n_bins, r->bins_allocated)));
     }
-    r->bins_allocated = ctx->scene.n_bins;
+    r->bins_allocated = std::max(ctx->scene.n_bins, r->bins_allocated);
   }
   IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px_hidden * 32, ctx->stream));
   IZ_CUDA(cudaMemsetAsync(r->d_total_rays, 0, 4 * sizeof(unsigned long long), ctx->stream));

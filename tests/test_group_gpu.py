@@ -83,8 +83,8 @@ def test_shared_cursor_two_contexts_one_device(ctx):
     spec = scenes.cornell_box(1.0)
     hs = cuda.HostScene(spec)
     ctx.upload(hs)
-    w = h = 200  # common.Tiles -> 25 x 25 tiles, 64 tiles
-    spp = 48
+    w = h = 400  # common.Tiles -> 25 x 25 tiles, 256 tiles
+    spp = 64
     full, rays = ctx.render(w, h, spp, seed=21)
     other = cuda.Context(0)
     try:
@@ -93,10 +93,12 @@ def test_shared_cursor_two_contexts_one_device(ctx):
         cursor = np.zeros(1, dtype=np.uint64)
         L = cuda.lib()
         out = {}
+        ready = threading.Barrier(2)  # the first setup of a context allocates its buffers: start pulling tiles together
 
         def work(name, c):
             cfg = cuda.RenderConfig(width=w, height=h, spp=spp, max_depth=50, sampler=cuda.SAMPLER_COLOUR, sample_offset=0, sample_count=spp, seed=21)
             cuda.check(L.izpi_render_setup(c._h, C.byref(cfg)))
+            ready.wait()
             cuda.check(L.izpi_render_tiles_shared(c._h, len(tiles), tiles.ctypes.data, cursor.ctypes.data, 2, None))
             out[name] = c.render_finish(w, h)
 
