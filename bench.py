@@ -181,10 +181,11 @@ def bench_render(ctx, cuda, scenes, world, rank, barrier, args):
         if args.no_4k and str(cfg_id).startswith("5"):
             continue
         spec = None
-        t_build = t_upload = 0.0
+        t_build = t_upload = t_make = 0.0
         if rank == 0:
             t0 = time.perf_counter()
             spec = make()
+            t_make = time.perf_counter() - t0
             hs = cuda.HostScene(spec, threads=os.cpu_count() or 8)
             t_build = time.perf_counter() - t0
             t0 = time.perf_counter()
@@ -195,7 +196,7 @@ def bench_render(ctx, cuda, scenes, world, rank, barrier, args):
         t0 = time.perf_counter()
         render.replicate_scene(ctx, 0)
         t_repl = time.perf_counter() - t0
-        render.New(ctx, w, h, 1, 50, sampler_type=sampler, seed=3).Render()  # warm-up: allocations, module load, cursor
+        render.New(ctx, w, h, spp, 50, sampler_type=sampler, seed=3, sample_count=1).Render()  # warm-up: ONE sample of the same frame (its buffers, module load, cursor)
         r = render.New(ctx, w, h, spp, 50, sampler_type=sampler, seed=3)
         if rank == 0:
             r.canvas()
@@ -216,7 +217,7 @@ def bench_render(ctx, cuda, scenes, world, rank, barrier, args):
                      "mrays_per_s": r.num_rays / dt / 1e6, "rays_per_sample": r.num_rays / (w * h * spp), "seconds": dt, "scaling": "strong",
                      "n_gpus": world, "primitives": n_prims, "gpu_launches_rank0": int(ctx.launches - l0),
                      "frame_ms_max_over_ranks": {"setup": tm[0], "tiles": tm[1], "merge_nccl_reduce": tm[2], "epilogue_and_d2h": tm[3]},
-                     "scene_s": {"build_rank0": t_build, "upload_rank0": t_upload, "replicate_nccl": t_repl},
+                     "scene_s": {"generate_rank0": t_make, "constructors_and_bvh_rank0": t_build - t_make, "upload_rank0": t_upload, "replicate_nccl": t_repl},
                      "canvas_sha256": hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest(),
                      "mean_rgb": [float(x) for x in img[1:, :, :3].mean(axis=(0, 1))]}
         if world == 1 and not args.no_render_stats:
@@ -224,7 +225,8 @@ def bench_render(ctx, cuda, scenes, world, rank, barrier, args):
             # kernels (SURVEY.md 8d formula, same as config 2), device time from CUDA events around every extend launch of a frame
             # rendered with ONE batch in flight (so that a launch's time is its own), both at a reduced sample count (the per-ray
             # statistics do not depend on it).
-            s_spp = max(1, min(spp, max(4, spp // 16)))
+            # enough samples for full batches (64 M paths on the large trees): small frames are launch-bound, not kernel-bound
+            s_spp = max(1, min(spp, max(4, spp // 16, -(-(1 << 26) // (w * h)))))
             rs = render.New(ctx, w, h, s_spp, 50, sampler_type=sampler, seed=3, stats=cuda.RENDER_STATS)
             rs.Render()
             st = ctx.render_stats()
@@ -495,6 +497,18 @@ def main():
     total_ms = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
 
+    # what the link gives: one plain pinned-host -> device copy of the step's rays (the e2e leg cannot beat it)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch = torch.empty_like(d_org)
+    scratch.copy_(h_org, non_blocking=True)
+    p0.record()
+    for _ in range(3):
+        scratch.copy_(h_org, non_blocking=True)
+    p1.record()
+    torch.cuda.synchronize()
+    pcie_h2d_gbs = 3 * h_org.numel() * 8 / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    del scratch
+
     # end to end through the C ABI with pinned host buffers: H2D of the rays + D2H of ids/t inside the timed region
     np_org, np_dir, np_ids, np_t = h_org.numpy(), h_dir.numpy(), h_ids.numpy(), h_t.numpy()
     for _ in range(2):
@@ -585,7 +599,7 @@ def main():
                                "mrays_per_s_at_hbm_peak": hbm * 1e3 / bytes_per_ray,
                                "note": "the byte side is the slower (binding) one; peaks measured by izpi_debug_fma_peak on this GPU"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 12,
-                    "h2d_gbs_per_rank": e2e_value / world * 48e6 / 1e9, "host_numa": numas},
+                    "h2d_gbs_per_rank": e2e_value / world * 48e6 / 1e9, "plain_pinned_h2d_copy_gbs_rank0": pcie_h2d_gbs, "host_numa": numas},
             "gpu_launches": int(launches),
             "render": render_info,
             "lbvh_tree": lbvh_info,

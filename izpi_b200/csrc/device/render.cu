@@ -1077,7 +1077,7 @@ int setup_one(izpi_ctx* ctx, const izpi_render_config* cfg) {
   LaunchCfg lc0;
   if ((rc = launch_cfg(ctx, lc0)) != IZPI_OK) return rc;
   int64_t want_cap = r->batch_paths_env ? r->batch_paths_env : (lc0.use_g4 ? (int64_t)1 << 26 : (int64_t)1 << 24);
-  const int64_t frame_paths = (int64_t)n_px * (int64_t)std::max(1, cfg->sample_count);
+  const int64_t frame_paths = (int64_t)n_px * (int64_t)std::max(1, cfg->spp);  // by spp, not sample_count: a one-sample warm-up of the frame allocates the frame's buffers
   if (frame_paths < want_cap) want_cap = std::max<int64_t>(frame_paths, 1 << 16);
   if (want_cap > r->slot[0].q.capacity || ctx->scene.n_bins > r->bins_allocated) {
     const int32_t cap = (int32_t)std::max<int64_t>(want_cap, r->slot[0].q.capacity);

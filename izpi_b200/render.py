@@ -196,8 +196,9 @@ class Renderer:
     share one."""
 
     def __init__(self, ctx: cuda.Context, size_x, size_y, num_samples, max_depth=50, background=(0.0, 0.0, 0.0),
-                 spectral_background=None, sampler_type=ColourSampler, seed=1, stats=False, dynamic=True):
+                 spectral_background=None, sampler_type=ColourSampler, seed=1, stats=False, dynamic=True, sample_count=None):
         self.ctx, self.size_x, self.size_y = ctx, size_x, size_y
+        self.sample_count = num_samples if sample_count is None else sample_count  # < num_samples: a partial (e.g. warm-up) pass of the frame
         self.num_samples, self.max_depth, self.sampler_type, self.seed = num_samples, max_depth, sampler_type, seed
         self.background, self.spectral_background = background, spectral_background
         self.stats, self.dynamic = int(stats), dynamic  # stats: 0 | cuda.RENDER_STATS | cuda.RENDER_TIMING (measurement modes)
@@ -207,7 +208,7 @@ class Renderer:
 
     def _config(self):
         cfg = cuda.RenderConfig(width=self.size_x, height=self.size_y, spp=self.num_samples, max_depth=self.max_depth,
-                                sampler=self.sampler_type, sample_offset=0, sample_count=self.num_samples, seed=self.seed,
+                                sampler=self.sampler_type, sample_offset=0, sample_count=self.sample_count, seed=self.seed,
                                 flags=int(self.stats))
         cfg.background[:] = [float(c) for c in self.background]
         self._keep = None
@@ -280,6 +281,6 @@ class Renderer:
 
 
 def New(ctx: cuda.Context, size_x, size_y, num_samples, max_depth=50, background=(0.0, 0.0, 0.0), spectral_background=None,
-        sampler_type=ColourSampler, seed=1, stats=False, dynamic=True) -> Renderer:
+        sampler_type=ColourSampler, seed=1, stats=False, dynamic=True, sample_count=None) -> Renderer:
     """render.New (renderer.go:73-106); the scene is the one uploaded to `ctx`."""
-    return Renderer(ctx, size_x, size_y, num_samples, max_depth, background, spectral_background, sampler_type, seed, stats, dynamic)
+    return Renderer(ctx, size_x, size_y, num_samples, max_depth, background, spectral_background, sampler_type, seed, stats, dynamic, sample_count)

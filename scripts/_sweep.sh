@@ -1,5 +1,11 @@
-python -m pytest tests/test_render_gpu.py tests/test_group_gpu.py -m gpu -x -q -k "same_path or aov or tile or depth or sorted or cursor or image" 2>&1 | tail -3
-python scripts/render_one.py --config 4 --spp 64 2>&1 | tail -1
-IZPI_LIB_PATH=variants/lib_plinline.so python scripts/render_one.py --config 4 --spp 64 2>&1 | tail -1
-python scripts/render_one.py --config 4 --spp 64 2>&1 | tail -1
-IZPI_LIB_PATH=variants/lib_plinline.so python scripts/render_one.py --config 4 --spp 64 2>&1 | tail -1
+python scripts/render_one.py --config 3 --spp 256 --repeat 3 2>&1 | tail -1
+python bench.py --no-cpu-baseline --render-configs 3 --steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+for e in d['render']: print(e['config'], e['spp'], e['msamples_per_s'], e['seconds'], e['frame_ms_max_over_ranks'])
+"
+python bench.py --no-cpu-baseline --render-configs 1,3 --no-render-stats --steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+for e in d['render']: print(e['config'], e['spp'], e['msamples_per_s'], e['seconds'], e['frame_ms_max_over_ranks'])
+"

@@ -48,7 +48,7 @@ def main():
     ctx.upload(hs)
     t_up = time.perf_counter() - t0
     if not args.no_warmup:
-        render.New(ctx, w, h, 1, 50, sampler_type=sampler, seed=3).Render()
+        render.New(ctx, w, h, args.spp, 50, sampler_type=sampler, seed=3, sample_count=1).Render()
     out = {"config": c, "spp": args.spp, "host_scene_build_s": t_build, "upload_s": t_up}
     best = None
     for _ in range(args.repeat):

@@ -24,7 +24,7 @@ for c in cfgs:
         os.environ["IZPI_BATCH_PATHS"] = str(1 << bp)
         ctx = cuda.Context(0)
         ctx.upload(hs)
-        render.New(ctx, w, h, 1, 50, sampler_type=sampler, seed=3).Render()
+        render.New(ctx, w, h, spp, 50, sampler_type=sampler, seed=3, sample_count=1).Render()
         r = render.New(ctx, w, h, spp, 50, sampler_type=sampler, seed=3)
         r.canvas()
         t0 = time.perf_counter()
