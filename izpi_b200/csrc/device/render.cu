@@ -731,7 +731,10 @@ __global__ void xyz_to_acescg_kernel(double* pix, long long n_px, double exposur
 // contexts (the members of a device group, or one-process-per-GPU ranks with the cursor in shared memory) claims the
 // next run of tiles with one atomic fetch-add whenever a slot has room -- the reference's workers pull work units from
 // one channel the same way (renderer.go:126-147) -- so nobody is handed a fixed share of cheap sky tiles or dear mesh tiles.
-constexpr int kSlots = 2;
+#ifndef IZPI_RENDER_SLOTS
+#define IZPI_RENDER_SLOTS 2
+#endif
+constexpr int kSlots = IZPI_RENDER_SLOTS;
 constexpr int kMaxBounces = 4096;
 
 __global__ void accumulate_traced_kernel(const unsigned long long* counters, unsigned long long* total) {

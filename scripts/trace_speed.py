@@ -18,8 +18,12 @@ def main():
     ap.add_argument("--rays", type=int, default=1 << 24)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--lbvh", action="store_true", help="BVH4 built on the device (izpi_bvh4_build) instead of the reference's tree")
     a = ap.parse_args()
     sc, lo, hi = scenes.closest_hit_scene()
+    if a.lbvh:
+        from izpi_b200 import scene as S
+        sc.bvh_builder = S.BVH_DEVICE_LBVH
     ctx = cuda.Context(0)
     ctx.upload(cuda.HostScene(sc))
     n = a.rays
