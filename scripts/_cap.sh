@@ -1,11 +1,5 @@
-M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,l1tex__t_sector_hit_rate.pct,smsp__thread_inst_executed_per_inst_executed.ratio,sm__warps_active.avg.pct_of_peak_sustained_active
-for c in "3 16" "4 16" "1 64"; do
-  set -- $c
-  tag=cfg$1
-  python scripts/render_one.py --config $1 --spp $2 --no-warmup --stats > gpurun_out/r02_cap_${tag}_plain.log 2>&1 && \
-  ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r02_cap_${tag}.csv python scripts/render_one.py --config $1 --spp $2 --no-warmup --stats > gpurun_out/r02_cap_${tag}_ncu.log 2>&1
-  tail -n 1 gpurun_out/r02_cap_${tag}_plain.log
-done
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-render > gpurun_out/r02_bench_norender.json 2> gpurun_out/plain_bench.log && \
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-render > gpurun_out/ncu_bench.json 2> gpurun_out/ncu_bench.log
+python scripts/render_one.py --config 5 --spp 4 --no-warmup > gpurun_out/plain5.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:extend_g2 -c 2 -o gpurun_out/r02_prof_cfg5_extend python scripts/render_one.py --config 5 --spp 4 --no-warmup > gpurun_out/ncu5.log 2>&1
+python scripts/render_one.py --config 4 --spp 4 --no-warmup > gpurun_out/plain4.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"shade_kernel|extend_kernel" -c 8 -o gpurun_out/r02_prof_cfg4_after python scripts/render_one.py --config 4 --spp 4 --no-warmup > gpurun_out/ncu4.log 2>&1
 echo done
