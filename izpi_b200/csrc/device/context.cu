@@ -259,6 +259,17 @@ static int upload_one(izpi_ctx* ctx, const izpi_scene_desc* d) {
     }
   }
   s.scalar_need = need_scalar;
+  for (int k = 0; k < 3; k++) { s.world_min[k] = 0.0f; s.world_max[k] = 1.0f; }
+  if (d->world_kind == IZPI_WORLD_BVH4 && d->n_nodes > 0) {
+    const izpi_bvh4_node& n0 = d->nodes[0];
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int k = 0; k < 4; k++) {
+      if (n0.child_index[k] == -1) continue;
+      const float lo[3] = {n0.min_x[k], n0.min_y[k], n0.min_z[k]}, hi[3] = {n0.max_x[k], n0.max_y[k], n0.max_z[k]};
+      for (int a = 0; a < 3; a++) { if (lo[a] < mn[a]) mn[a] = lo[a]; if (hi[a] > mx[a]) mx[a] = hi[a]; }
+    }
+    for (int a = 0; a < 3; a++) if (mx[a] > mn[a]) { s.world_min[a] = mn[a]; s.world_max[a] = mx[a]; }
+  }
   for (int i = 0; i < d->n_prims; i++) {
     const int m = (int)((d->prims[i].tag >> 4) & 0x3fffu);
     if (d->n_materials > 0 && m >= d->n_materials) { set_error("izpi_scene_upload: primitive record refers to a missing material"); return IZPI_EINVAL; }

@@ -35,6 +35,7 @@ struct DScene {
   int32_t g4_need;              // most stack entries a ray can need in THIS tree (<= 64, bvh4.go:71); picks the slab size of the 2-lane kernel
   int32_t class_mask;           // bit c set <=> some primitive carries a material of class c (IZPI_MAT_*): shade launches of absent classes are skipped
   int32_t n_textures, n_spectex;
+  float world_min[3], world_max[3];  // union of the root node's child boxes (BVH4 worlds): quantises ray origins for the coherence sort
   int32_t scalar_need;          // stack entries the thread-per-ray traversal can need in this tree (<= 64): sizes its shared-memory stack
   int32_t pad0;
   // Material bins of the wavefront renderer (north_star 3: paths sorted by material ID between bounces).  A hit is filed

@@ -16,6 +16,8 @@
 #include <cstring>
 #include <deque>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../../include/izpi_host.h"
 #include "intersect_g2.cuh"
 #include "shade.cuh"
@@ -55,6 +57,7 @@ struct RenderParams {
 struct Queues {
   int32_t* cur;                 // live paths entering this bounce
   int32_t* next;                // survivors
+  uint32_t* next_keys;          // coherence keys of the survivors, same positions as `next` (nullptr: the scene is not sorted)
   int32_t* bins;                // [n_bins][capacity]
   unsigned long long* counters; // [0] cur count, [1] next count, [7] work head, [8] rays traced, [9] nodes visited, [10] primitive tests (counting kernels), [kBinCounters + b] count of bin b
   int32_t capacity;
@@ -67,10 +70,11 @@ __device__ __forceinline__ DRay path_ray(const PathState& p) {
 }
 
 // Warp-aggregated append: lanes with `want` and the same `cls` share one atomicAdd.
-__device__ __forceinline__ void push_binned(bool want, int cls, int32_t value, int32_t* base, int stride,
-                                            unsigned long long* counts) {
+// Returns the position written (within the bin), -1 for lanes that did not push.
+__device__ __forceinline__ long long push_binned(bool want, int cls, int32_t value, int32_t* base, int stride,
+                                                 unsigned long long* counts) {
   unsigned active = __ballot_sync(0xffffffffu, want);
-  if (!want) return;
+  if (!want) return -1;
   unsigned peers = __match_any_sync(active, cls);
   int leader = __ffs(peers) - 1;
   unsigned lane = threadIdx.x & 31u;
@@ -79,6 +83,37 @@ __device__ __forceinline__ void push_binned(bool want, int cls, int32_t value, i
   slot = __shfl_sync(peers, slot, leader);
   int rank = __popc(peers & ((1u << lane) - 1u));
   base[(size_t)cls * stride + slot + rank] = value;
+  return (long long)(slot + rank);
+}
+
+// Coherence key of a ray (see the sort below): low bits of the primitive the ray leaves, cell of the origin over the root box,
+// cell of the direction (2 bits per axis of d / |d|_inf, sign included).
+#ifndef IZPI_SORT_KEY
+#define IZPI_SORT_KEY 0  // the three layouts measure the same on config 4 (127.6 / 128.8 / 129.0 Msamples/s); the 16-bit one sorts in two passes
+#endif
+#if IZPI_SORT_KEY == 0    // 1 bit of the primitive | 3 bits of origin per axis | 2 bits of direction per axis
+constexpr int kSortKeyBits = 16, kKeyPrimBits = 1, kKeyPosBits = 3;
+#elif IZPI_SORT_KEY == 1  // 4 | 2 | 2
+constexpr int kSortKeyBits = 16, kKeyPrimBits = 4, kKeyPosBits = 2;
+#else                     // 5 | 3 | 2: three radix passes
+constexpr int kSortKeyBits = 20, kKeyPrimBits = 5, kKeyPosBits = 3;
+#endif
+__device__ __forceinline__ uint32_t coherence_key(const DScene& sc, int32_t prim, d3 o, d3 d) {
+  uint32_t key = ((uint32_t)prim & ((1u << kKeyPrimBits) - 1u)) << (3 * kKeyPosBits + 6);
+  const double ov[3] = {o.x, o.y, o.z}, dv[3] = {d.x, d.y, d.z};
+  double dm = fmax(fabs(dv[0]), fmax(fabs(dv[1]), fabs(dv[2])));
+  if (!(dm > 0)) dm = 1.0;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    float f = ((float)ov[a] - sc.world_min[a]) / (sc.world_max[a] - sc.world_min[a]);
+    int c = (int)(f * (float)(1 << kKeyPosBits));
+    c = c < 0 ? 0 : (c > (1 << kKeyPosBits) - 1 ? (1 << kKeyPosBits) - 1 : c);
+    int q = (int)((dv[a] / dm + 1.0) * 2.0);
+    q = q < 0 ? 0 : (q > 3 ? 3 : q);
+    key |= (uint32_t)c << (6 + kKeyPosBits * a);
+    key |= (uint32_t)q << (2 * a);
+  }
+  return key;
 }
 
 // ---- ray generation -------------------------------------------------------------------------
@@ -617,8 +652,23 @@ shade_kernel(const __grid_constant__ DScene sc, RenderParams rp, PathState* path
       }
       }  // integrators
     }
-    push_binned(survive, 0, pi, q.next, q.capacity, q.counters + 1);
+    const long long pos = push_binned(survive, 0, pi, q.next, q.capacity, q.counters + 1);
+    if (pos >= 0 && q.next_keys) {
+      const PathState& p = paths[pi];  // the scattered ray written above (still in L1)
+      q.next_keys[pos] = coherence_key(sc, p.hit_rec, mk(p.ox, p.oy, p.oz), mk(p.dx, p.dy, p.dz));
+    }
   }
+}
+
+// ---- coherence sort (tiny, specular scenes) ----------------------------------------------------
+// After two bounces the live rays of a scene like config 4 are incoherent: the thread-per-ray traversal and the dielectric
+// shade (whose nested path-length trace is a second traversal) then run at ~15 of 32 active lanes.  Sorting the queue by
+// (surface the ray leaves, origin cell, direction cell) puts rays that walk the same nodes and hit the same primitive into
+// the same warp.  Paths are independent and keyed by (pixel, sample), so the order in which a bounce processes them changes
+// nothing in the image.  `n_bound` is the host's (stale, >=) count; entries past the device's own count get the last key.
+__global__ void sort_pad_kernel(const unsigned long long* __restrict__ counters, int n_bound, uint32_t* __restrict__ keys) {
+  const int i = (int)counters[0] + blockIdx.x * blockDim.x + threadIdx.x;  // entries past the device's own count sort to the end
+  if (i < n_bound) keys[i] = 0xffffffffu;
 }
 
 // swap queues between bounces without a host round trip
@@ -746,6 +796,11 @@ struct BatchSlot {
   Queues q{};
   uint32_t* d_pixels = nullptr;
   int64_t pixel_capacity = 0;
+  uint32_t *d_keys_cur = nullptr, *d_keys_alt = nullptr;  // coherence sort: keys of the `cur` queue, CUB's key output (q.next_keys is the third buffer)
+  int32_t* d_sorted = nullptr;                            // third queue buffer: where the sorted order lands
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  int64_t sort_capacity = 0;
   unsigned long long* h_count = nullptr;  // pinned + mapped: advance_kernel writes the live count of bounce b to [b & 7]
   unsigned long long* d_count_mapped = nullptr;
   cudaStream_t stream = nullptr;
@@ -790,6 +845,7 @@ void render_state_free(izpi_ctx* ctx) {
   cudaFree(r->d_canvas); cudaFree(r->d_out); cudaFree(r->d_snap); cudaFree(r->d_bg); cudaFree(r->d_total_rays);
   for (BatchSlot& s : r->slot) {
     cudaFree(s.d_paths); cudaFree(s.d_pixels); cudaFree(s.q.cur); cudaFree(s.q.next); cudaFree(s.q.bins); cudaFree(s.q.counters);
+    cudaFree(s.d_keys_cur); cudaFree(s.d_keys_alt); cudaFree(s.q.next_keys); cudaFree(s.d_sorted); cudaFree(s.d_sort_tmp);
     if (s.h_count) cudaFreeHost(s.h_count);
     for (cudaEvent_t e : s.ev) if (e) cudaEventDestroy(e);
     if (s.resolved) cudaEventDestroy(s.resolved);
@@ -822,7 +878,8 @@ int launch(izpi_ctx* ctx, cudaStream_t st, K kern, dim3 grid, dim3 block, size_t
 }
 
 struct LaunchCfg {
-  bool use_g4, use_g2, g2_deep, count;
+  bool use_g4, use_g2, g2_deep, count, sort_rays;
+  long long sort_min;
   size_t smem, smem4, smem2;
   int ext_blocks, ext4_blocks, ext2_blocks;
 };
@@ -858,6 +915,10 @@ int launch_cfg(izpi_ctx* ctx, LaunchCfg& lc) {
   lc.use_g4 = ctx->scene.world_kind == IZPI_WORLD_BVH4 && ctx->scene.g4_ok && !ctx->force_scalar && ctx->scene.n_nodes >= coop_min_nodes;
   lc.use_g2 = lc.use_g4 && ctx->trace_lanes == 2 && ctx->scene.g4_need <= kG2StackDeep;
   lc.count = ctx->render && ctx->render->count_on;
+  // coherence sort: thread-per-ray BVH worlds only (the cooperative kernels do not need it, slices have no origin cells)
+  lc.sort_rays = !lc.use_g4 && ctx->scene.world_kind == IZPI_WORLD_BVH4;
+  lc.sort_min = 1 << 18;
+  if (const char* e = getenv("IZPI_SORT_RAYS")) { long v = atol(e); if (v <= 0) lc.sort_rays = false; else if (v > 1) lc.sort_min = v; }
   return IZPI_OK;
 }
 
@@ -925,6 +986,19 @@ int batch_step(izpi_ctx* ctx, RenderState* r, BatchSlot& s, const LaunchCfg& lc)
   }
   if (s.live == 0 || s.bounce > r->rp.max_depth || s.bounce >= kMaxBounces) { s.drained = true; return IZPI_OK; }
   int rc;
+  if (lc.sort_rays && s.d_sorted && s.bounce >= 2 && s.live >= (unsigned long long)lc.sort_min) {
+    // Coherence sort of this bounce's queue.  Its keys were written by the previous bounce's shade kernels next to the queue
+    // entries (Queues::next_keys, now s.d_keys_cur); entries between the device's own count and the host's stale bound get
+    // the largest key.  Two onesweep passes over (16-bit key, path index) pairs.
+    const int nb = (int)std::min<unsigned long long>(s.live, (unsigned long long)s.q.capacity);
+    if ((rc = span_begin(r, st, 2)) != IZPI_OK) return rc;
+    if ((rc = launch(ctx, st, sort_pad_kernel, dim3((nb + 255) / 256), dim3(256), 0, s.q.counters, nb, s.d_keys_cur)) != IZPI_OK) return rc;
+    size_t tmp = s.sort_tmp_bytes;
+    IZ_CUDA(cub::DeviceRadixSort::SortPairs(s.d_sort_tmp, tmp, s.d_keys_cur, s.d_keys_alt, s.q.cur, s.d_sorted, nb, 0, kSortKeyBits, st));
+    ctx->launches += 3;  // histogram + two onesweep passes
+    std::swap(s.q.cur, s.d_sorted);  // the sorted order is this bounce's queue; the old buffer becomes the next sort's output
+    if ((rc = span_end(r, st)) != IZPI_OK) return rc;
+  }
   if ((rc = span_begin(r, st, 0)) != IZPI_OK) return rc;
   long long want = ((long long)s.live + kThreads - 1) / kThreads;
   if (lc.use_g2) {
@@ -952,6 +1026,7 @@ int batch_step(izpi_ctx* ctx, RenderState* r, BatchSlot& s, const LaunchCfg& lc)
   if ((rc = launch_shade<IZPI_MAT_DIFFUSE_LIGHT>(ctx, r, s, sg)) != IZPI_OK) return rc;
   if ((rc = launch_shade<IZPI_MAT_PBR>(ctx, r, s, sg)) != IZPI_OK) return rc;
   std::swap(s.q.cur, s.q.next);
+  std::swap(s.d_keys_cur, s.q.next_keys);  // the survivors' keys follow their queue
   Queues qs = s.q;  // after the swap: cur = survivors; advance moves the count
   if ((rc = launch(ctx, st, advance_kernel, dim3(1), dim3(1), 0, qs, s.d_count_mapped + (s.bounce & 7))) != IZPI_OK) return rc;
   if ((rc = span_end(r, st)) != IZPI_OK) return rc;
@@ -1098,6 +1173,23 @@ int setup_one(izpi_ctx* ctx, const izpi_render_config* cfg) {
       IZ_CUDA(cudaMalloc(&s.q.bins, (size_t)s.q.capacity * 4 * (size_t)std::max(ctx->scene.n_bins, r->bins_allocated)));
     }
     r->bins_allocated = std::max(ctx->scene.n_bins, r->bins_allocated);
+  }
+  for (BatchSlot& s : r->slot) {  // coherence-sort buffers: only for scenes that are sorted, same capacity as the queues
+    if (lc0.sort_rays && s.sort_capacity < (int64_t)s.q.capacity) {
+      cudaFree(s.d_keys_cur); cudaFree(s.d_keys_alt); cudaFree(s.q.next_keys); cudaFree(s.d_sorted); cudaFree(s.d_sort_tmp);
+      s.d_keys_cur = s.d_keys_alt = s.q.next_keys = nullptr; s.d_sorted = nullptr; s.d_sort_tmp = nullptr; s.sort_capacity = 0;
+      const size_t cap = (size_t)s.q.capacity;
+      IZ_CUDA(cudaMalloc(&s.d_keys_cur, cap * 4)); IZ_CUDA(cudaMalloc(&s.d_keys_alt, cap * 4)); IZ_CUDA(cudaMalloc(&s.q.next_keys, cap * 4));
+      IZ_CUDA(cudaMalloc(&s.d_sorted, cap * 4));
+      s.sort_tmp_bytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, s.sort_tmp_bytes, s.d_keys_cur, s.d_keys_alt, s.q.cur, s.d_sorted, (int)cap, 0, kSortKeyBits, s.stream);
+      IZ_CUDA(cudaMalloc(&s.d_sort_tmp, s.sort_tmp_bytes));
+      s.sort_capacity = (int64_t)cap;
+    }
+    if (!lc0.sort_rays && s.q.next_keys) {  // a scene that is not sorted: the shade kernels must not write keys
+      cudaFree(s.d_keys_cur); cudaFree(s.d_keys_alt); cudaFree(s.q.next_keys); cudaFree(s.d_sorted); cudaFree(s.d_sort_tmp);
+      s.d_keys_cur = s.d_keys_alt = s.q.next_keys = nullptr; s.d_sorted = nullptr; s.d_sort_tmp = nullptr; s.sort_capacity = 0;
+    }
   }
   IZ_CUDA(cudaMemsetAsync(r->d_canvas, 0, n_px_hidden * 32, ctx->stream));
   IZ_CUDA(cudaMemsetAsync(r->d_total_rays, 0, 4 * sizeof(unsigned long long), ctx->stream));
