@@ -37,21 +37,6 @@ def tile_list(size_x: int, size_y: int) -> np.ndarray:
     return np.stack([tx * sx, ty * sy, tx * sx + (sx - 1), ty * sy + (sy - 1)], axis=1).astype(np.uint32)
 
 
-def spread_tiles(tiles: np.ndarray) -> np.ndarray:
-    """The tile list in a fixed pseudo-random order (the same on every rank): a run of consecutive entries is then a mix of
-    cheap and expensive tiles -- sky and mesh, wall and glass -- instead of a horizontal band of the image, so equal-sized
-    claims from the shared cursor cost about the same and the guided schedule ends evenly.  The reference walks its grid in a
-    spiral from the centre (grid.WalkGrid, grid.go:27) for the preview's sake; pixels are disjoint, so any order gives the
-    same canvas."""
-    n = len(tiles)
-    if n < 3:
-        return tiles
-    step = max(2, int(n * 0.6180339887))
-    while np.gcd(step, n) != 1:
-        step += 1
-    return np.ascontiguousarray(tiles[(np.arange(n, dtype=np.int64) * step) % n])
-
-
 def shard_tiles(tiles: np.ndarray, world: int, rank: int) -> np.ndarray:
     """Static round-robin deal of the tile list (rank r renders tiles r, r+world, ...): the fallback when the ranks have no
     shared cursor.  The default is dynamic dealing, see TileCursor."""
@@ -258,8 +243,6 @@ class Renderer:
         cuda.check(L.izpi_render_setup(h, C.byref(cfg)))
         t1 = time.perf_counter()
         tiles = tile_list(self.size_x, self.size_y)
-        if world > 1:
-            tiles = spread_tiles(tiles)
         cursor = shared_cursor() if (world > 1 and self.dynamic) else None
         if world > 1 and cursor is None:
             mine = shard_tiles(tiles, world, rank)

@@ -1,5 +1,5 @@
-python -m pytest tests/test_trace_gpu.py tests/test_bvh_device.py -m gpu -x -q 2>&1 | tail -3
-IZPI_RAYF_PREPASS=0 python scripts/trace_speed.py --reps 5 2>&1 | tail -1
-python scripts/trace_speed.py --reps 5 2>&1 | tail -1
-IZPI_RAYF_PREPASS=0 python scripts/trace_speed.py --reps 5 --lbvh 2>&1 | tail -1
-python scripts/trace_speed.py --reps 5 --lbvh 2>&1 | tail -1
+for L in "" variants/lib_key0.so variants/lib_key2.so; do
+echo "== $L"
+IZPI_LIB_PATH=$L python scripts/render_one.py --config 4 --spp 64 --repeat 2 --stats 2>&1 | tail -1
+IZPI_LIB_PATH=$L python scripts/render_one.py --config 4 --spp 64 --repeat 3 2>&1 | tail -1
+done

@@ -41,15 +41,6 @@ def test_shards_partition_tiles(world):
     assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
 
 
-def test_spread_tiles_is_a_permutation():
-    for w, h in ((3840, 2160), (1024, 1024), (400, 400), (40, 60)):
-        t = render.tile_list(w, h)
-        s = render.spread_tiles(t)
-        assert s.shape == t.shape and len(np.unique(s, axis=0)) == len(t)
-        if len(t) > 100:  # consecutive entries are far apart in the image
-            assert (np.abs(np.diff(s[:, 1].astype(np.int64))) > 0).mean() > 0.9
-
-
 def test_tiles_error_when_nothing_divides():
     from izpi_b200 import cuda
     with pytest.raises(cuda.IzpiError):
