@@ -34,15 +34,16 @@ sys.path.insert(0, ROOT)
 
 N_RAYS = 1 << 24
 WORKLOAD = "closest-hit: 1M-triangle displaced torus (BVH4, LCG seed 12345), 16,777,216 incoherent rays/step, fp64 exact"
-KERNEL_SOURCES = ["izpi_b200/csrc/device/trace.cu", "izpi_b200/csrc/device/render.cu", "izpi_b200/csrc/device/intersect.cuh",
-                  "izpi_b200/csrc/device/intersect_g2.cuh", "izpi_b200/csrc/device/intersect_g4.cuh", "izpi_b200/csrc/device/shade.cuh",
-                  "izpi_b200/csrc/device/shade_textures.cuh", "izpi_b200/csrc/device/dscene.cuh", "izpi_b200/csrc/device/context.cu"]
+TRACE_SOURCES = ["izpi_b200/csrc/device/trace.cu", "izpi_b200/csrc/device/intersect.cuh", "izpi_b200/csrc/device/intersect_g2.cuh",
+                 "izpi_b200/csrc/device/intersect_g4.cuh", "izpi_b200/csrc/device/dscene.cuh", "izpi_b200/csrc/device/context.cu"]
+RENDER_SOURCES = TRACE_SOURCES + ["izpi_b200/csrc/device/render.cu", "izpi_b200/csrc/device/shade.cuh", "izpi_b200/csrc/device/shade_textures.cuh"]
 
 
-def kernel_source_hash():
-    """sha256 over the kernel sources: an ncu capture describes the kernels of ONE source state."""
+def kernel_source_hash(key="render"):
+    """sha256 over the sources of the kernels an ncu capture describes: the closest-hit kernels (keys `trace_*`) or the whole
+    renderer (keys `render_*`).  A capture is valid for ONE source state."""
     h = hashlib.sha256()
-    for f in KERNEL_SOURCES:
+    for f in (TRACE_SOURCES if key.startswith("trace") else RENDER_SOURCES):
         with open(os.path.join(ROOT, f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -57,7 +58,7 @@ def ncu_traffic(key, units):
         t = json.load(open(p))[key]
     except Exception:
         return None, None, "no ncu capture committed for this kernel"
-    if t.get("source_sha256") != kernel_source_hash():
+    if t.get("source_sha256") != kernel_source_hash(key):
         return None, t.get("kernel"), "stale: kernel sources changed after the ncu capture (profiles/r02_traffic.json)"
     return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (units / t["units_per_launch"]), t.get("kernel"), t.get("source")
 

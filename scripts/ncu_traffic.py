@@ -80,7 +80,7 @@ def main():
                     "dram_bytes_per_unit": (tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"]) / args.units,
                     "lts_hit_rate_pct_mean": (sum(hits) / len(hits)) if hits else None,
                     "source": f"{os.path.basename(args.csv)} (ncu --clock-control none; launches summed: {launches}) {args.note}".strip(),
-                    "source_sha256": bench.kernel_source_hash()}
+                    "source_sha256": bench.kernel_source_hash(args.key)}
     json.dump(db, open(p, "w"), indent=1)
     print(json.dumps(db[args.key], indent=1))
 
