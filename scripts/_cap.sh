@@ -1,5 +1,7 @@
-python scripts/render_one.py --config 5 --spp 4 --no-warmup > gpurun_out/plain5.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:extend_g2 -c 2 -o gpurun_out/r02_prof_cfg5_extend python scripts/render_one.py --config 5 --spp 4 --no-warmup > gpurun_out/ncu5.log 2>&1
-python scripts/render_one.py --config 4 --spp 4 --no-warmup > gpurun_out/plain4.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"shade_kernel|extend_kernel" -c 8 -o gpurun_out/r02_prof_cfg4_after python scripts/render_one.py --config 4 --spp 4 --no-warmup > gpurun_out/ncu4.log 2>&1
-echo done
+M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct
+for c in "4 16" "1 64"; do
+  set -- $c
+  python scripts/render_one.py --config $1 --spp $2 --no-warmup --stats > gpurun_out/r02_cap_cfg$1_plain.log 2>&1 && \
+  timeout 200 ncu --metrics $M --clock-control none -k regex:extend_ --csv --log-file gpurun_out/r02_cap_cfg$1.csv python scripts/render_one.py --config $1 --spp $2 --no-warmup --stats > gpurun_out/r02_cap_cfg$1_ncu.log 2>&1
+  tail -n 1 gpurun_out/r02_cap_cfg$1_plain.log | cut -c1-400
+done
