@@ -282,9 +282,13 @@ def cpu_render_baseline(spec, w, h, spp, sampler, gpu_msamples):
     t0 = time.perf_counter()
     _, crays = osn.render(w, h, cspp, sampler=sampler, rng_mode=0, seed=3, window=win, epilogue=False)
     dt = time.perf_counter() - t0
-    # scale the sample so that it is a few seconds of host work
+    # size the sample for about 3 s of host work: more samples per pixel first (up to the frame's), then more rows
     if dt < 2.0:
-        cspp = int(min(spp, max(cspp, cspp * 4.0 / max(dt, 1e-3))))
+        want = 3.0 / max(dt, 1e-4) * (w * rows * cspp)
+        cspp = int(min(spp, max(cspp, want / (w * rows))))
+        rows = int(min(h - 2, max(rows, want / (w * cspp))))
+        y0 = max(1, h // 2 - rows // 2)
+        win = (0, y0, w - 1, y0 + rows - 1)
         t0 = time.perf_counter()
         _, crays = osn.render(w, h, cspp, sampler=sampler, rng_mode=0, seed=3, window=win, epilogue=False)
         dt = time.perf_counter() - t0
