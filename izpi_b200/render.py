@@ -16,6 +16,7 @@ spiral only serves the live preview; every order produces the same canvas.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -35,6 +36,45 @@ def tile_list(size_x: int, size_y: int) -> np.ndarray:
     ty, tx = np.meshgrid(np.arange(gy, dtype=np.uint32), np.arange(gx, dtype=np.uint32), indexing="ij")
     tx, ty = tx.ravel(), ty.ravel()
     return np.stack([tx * sx, ty * sy, tx * sx + (sx - 1), ty * sy + (sy - 1)], axis=1).astype(np.uint32)
+
+
+def walk_grid_spiral(size_x: int, size_y: int) -> np.ndarray:
+    """grid.WalkGrid(sizeX, sizeY, PATTERN_SPIRAL) (internal/grid/grid.go:27-128), the order in which RendererImpl.Render queues
+    its work units (renderer.go:151,172): start at the centre cell, try to turn at every step (up, right, down, left, ...),
+    keep going straight while the cell in the new direction has been walked already; cells outside the grid are walked but not
+    emitted.  Returns (n, 2) int32 grid positions."""
+    total = size_x * size_y
+    if total <= 0:
+        return np.zeros((0, 2), dtype=np.int32)
+    step = ((0, -1), (1, 0), (0, 1), (-1, 0))  # up, right, down, left
+    x, y = size_x // 2, size_y // 2
+    seen = {(x, y)}
+    path = [(x, y)]
+    k = 0
+    while len(path) < total:
+        dx, dy = step[k % 4]
+        nxt = (x + dx, y + dy)
+        if nxt in seen:
+            k -= 1
+            continue
+        x, y = nxt
+        seen.add(nxt)
+        if 0 <= x < size_x and 0 <= y < size_y:
+            path.append(nxt)
+        k += 1
+    return np.asarray(path, dtype=np.int32)
+
+
+def spiral_tiles(size_x: int, size_y: int) -> np.ndarray:
+    """tile_list() in the reference's queueing order (walk_grid_spiral over the tile grid): centre of the image first, border
+    last.  Pixels are disjoint, so the canvas does not depend on the order; the shared cursor deals runs of THIS list, so the
+    large early claims are the (usually expensive) middle of the frame and the short final claims its (usually cheap) rim."""
+    sx, sy = cuda.tiles(size_x, size_y)
+    if sx == 0 or sy == 0:
+        raise cuda.IzpiError(cuda.EINVAL, "no tile size divides the image dimensions (common.Tiles)")
+    g = walk_grid_spiral(size_x // sx, size_y // sy).astype(np.uint32)
+    tx, ty = g[:, 0], g[:, 1]
+    return np.ascontiguousarray(np.stack([tx * sx, ty * sy, tx * sx + (sx - 1), ty * sy + (sy - 1)], axis=1).astype(np.uint32))
 
 
 def shard_tiles(tiles: np.ndarray, world: int, rank: int) -> np.ndarray:
@@ -201,6 +241,7 @@ class Renderer:
         self.sample_count = num_samples if sample_count is None else sample_count  # < num_samples: a partial (e.g. warm-up) pass of the frame
         self.num_samples, self.max_depth, self.sampler_type, self.seed = num_samples, max_depth, sampler_type, seed
         self.background, self.spectral_background = background, spectral_background
+        self.walk = os.environ.get("IZPI_TILE_WALK", "linear")  # "spiral": the reference's queueing order (grid.WalkGrid)
         self.stats, self.dynamic = int(stats), dynamic  # stats: 0 | cuda.RENDER_STATS | cuda.RENDER_TIMING (measurement modes)
         self.num_rays = 0
         self.timings = {}
@@ -242,7 +283,7 @@ class Renderer:
         cfg = self._config()
         cuda.check(L.izpi_render_setup(h, C.byref(cfg)))
         t1 = time.perf_counter()
-        tiles = tile_list(self.size_x, self.size_y)
+        tiles = spiral_tiles(self.size_x, self.size_y) if self.walk == "spiral" else tile_list(self.size_x, self.size_y)
         cursor = shared_cursor() if (world > 1 and self.dynamic) else None
         if world > 1 and cursor is None:
             mine = shard_tiles(tiles, world, rank)

@@ -41,6 +41,20 @@ def test_shards_partition_tiles(world):
     assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
 
 
+def test_walk_grid_spiral_matches_the_reference_order():
+    """grid.walkGridSpiral (grid.go:48-128): centre first, then up, right, down, down, left, left, up, up, up, ...; every cell
+    once; cells outside a non-square grid are skipped."""
+    p = render.walk_grid_spiral(3, 3)
+    assert p.tolist() == [[1, 1], [1, 0], [2, 0], [2, 1], [2, 2], [1, 2], [0, 2], [0, 1], [0, 0]]
+    for gx, gy in ((120, 90), (32, 32), (16, 16), (1, 5), (4, 1)):
+        p = render.walk_grid_spiral(gx, gy)
+        assert len(p) == gx * gy and len({(int(a), int(b)) for a, b in p}) == gx * gy
+        assert p[0].tolist() == [gx // 2, gy // 2]
+        assert (p[:, 0] >= 0).all() and (p[:, 0] < gx).all() and (p[:, 1] >= 0).all() and (p[:, 1] < gy).all()
+    t = render.spiral_tiles(3840, 2160)
+    assert len(t) == 10800 and len(np.unique(t, axis=0)) == 10800
+
+
 def test_tiles_error_when_nothing_divides():
     from izpi_b200 import cuda
     with pytest.raises(cuda.IzpiError):
