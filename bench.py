@@ -246,7 +246,9 @@ def bench_render(ctx, cuda, scenes, world, rank, barrier, args):
             key = f"render_cfg{cfg_id}_extend"
             traffic, tk, tsrc = ncu_traffic(key, rays)
             entry["roofline"] = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                                 "frac": (achieved / hbm) if achieved else None, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
+                                 "frac": (achieved / hbm) if achieved else None, "traffic": traffic, "traffic_per_ray": (traffic / rays) if traffic else None,
+                                 "traffic_note": "DRAM bytes of all extend launches of the measured frame (ncu bytes per ray x its rays)",
+                                 "traffic_source": tsrc, "peak_source": peak_src,
                                  "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": st["nodes_visited"] / rays,
                                  "prim_tests_per_ray": st["prim_tests"] / rays, "measured_at_spp": s_spp,
                                  "extend_ms": tt_["extend_ms"], "shade_ms": tt_["shade_ms"], "raygen_resolve_ms": tt_["other_ms"],
