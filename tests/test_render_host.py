@@ -41,11 +41,23 @@ def test_shards_partition_tiles(world):
     assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
 
 
-def test_walk_grid_spiral_matches_the_reference_order():
-    """grid.walkGridSpiral (grid.go:48-128): centre first, then up, right, down, down, left, left, up, up, up, ...; every cell
-    once; cells outside a non-square grid are skipped."""
-    p = render.walk_grid_spiral(3, 3)
-    assert p.tolist() == [[1, 1], [1, 0], [2, 0], [2, 1], [2, 2], [1, 2], [0, 2], [0, 1], [0, 0]]
+# TestWalkGridSpiral (internal/grid/grid_test.go:9-80): the reference's own expected paths for 3x3, 4x4 and 5x5 grids
+_SPIRAL_GOLDEN = {
+    (3, 3): [(1, 1), (1, 0), (2, 0), (2, 1), (2, 2), (1, 2), (0, 2), (0, 1), (0, 0)],
+    (4, 4): [(2, 2), (2, 1), (3, 1), (3, 2), (3, 3), (2, 3), (1, 3), (1, 2), (1, 1), (1, 0), (2, 0), (3, 0), (0, 3), (0, 2), (0, 1), (0, 0)],
+    (5, 5): [(2, 2), (2, 1), (3, 1), (3, 2), (3, 3), (2, 3), (1, 3), (1, 2), (1, 1), (1, 0), (2, 0), (3, 0), (4, 0), (4, 1), (4, 2), (4, 3),
+             (4, 4), (3, 4), (2, 4), (1, 4), (0, 4), (0, 3), (0, 2), (0, 1), (0, 0)],
+}
+
+
+@pytest.mark.parametrize("size", sorted(_SPIRAL_GOLDEN))
+def test_walk_grid_spiral_golden(size):
+    assert [tuple(int(v) for v in p) for p in render.walk_grid_spiral(*size)] == _SPIRAL_GOLDEN[size]
+
+
+def test_walk_grid_spiral_covers_any_grid():
+    """Every cell once, centre first, also for non-square grids (cells outside the grid are walked but not emitted,
+    grid.go:60-128); the tile list in that order is a permutation of the row-major one."""
     for gx, gy in ((120, 90), (32, 32), (16, 16), (1, 5), (4, 1)):
         p = render.walk_grid_spiral(gx, gy)
         assert len(p) == gx * gy and len({(int(a), int(b)) for a, b in p}) == gx * gy
@@ -53,6 +65,7 @@ def test_walk_grid_spiral_matches_the_reference_order():
         assert (p[:, 0] >= 0).all() and (p[:, 0] < gx).all() and (p[:, 1] >= 0).all() and (p[:, 1] < gy).all()
     t = render.spiral_tiles(3840, 2160)
     assert len(t) == 10800 and len(np.unique(t, axis=0)) == 10800
+    assert {tuple(r) for r in t.tolist()} == {tuple(r) for r in render.tile_list(3840, 2160).tolist()}
 
 
 def test_tiles_error_when_nothing_divides():
