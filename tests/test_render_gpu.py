@@ -80,6 +80,21 @@ def test_spectral_pyramid_same_path(ctx, oracle_mod):
     _same_path(ctx, oracle_mod, scenes.spectral_pyramid(1.0), 40, 40, 16, cuda.SAMPLER_SPECTRAL, jitter_probe=True)
 
 
+def test_coherence_sort_forced_same_path(ctx, oracle_mod):
+    """The coherence sort of the thread-per-ray wavefront (queue sorted by origin / direction cell between bounces) only kicks in
+    above 2^18 live paths; forced on for every bounce here (IZPI_SORT_RAYS=2), the frame still equals the oracle's pixel for
+    pixel, and the unsorted frame bit for bit."""
+    spec = scenes.spectral_pyramid(1.0)
+    os.environ["IZPI_SORT_RAYS"] = "2"
+    try:
+        sorted_img, _ = _same_path(ctx, oracle_mod, spec, 40, 40, 16, cuda.SAMPLER_SPECTRAL)
+        os.environ["IZPI_SORT_RAYS"] = "0"
+        plain, _ = ctx.render(40, 40, 16, sampler=cuda.SAMPLER_SPECTRAL, seed=5)
+    finally:
+        del os.environ["IZPI_SORT_RAYS"]
+    assert plain.tobytes() == sorted_img.tobytes()
+
+
 def test_pbr_mesh_same_path(ctx, oracle_mod):
     """Config 3 materials at test size: PBR with albedo/normal/roughness/metalness image textures."""
     sc = scenes.cornell_pbr_mesh(1.0, n_around=60, n_tube=40, tex_size=64)
