@@ -39,6 +39,13 @@ int izpi_host_scene_upload(const izpi_host_scene* s, izpi_ctx* ctx);
 /* common.Tiles (common/tiles.go:6-24); 0 when no listed size divides the dimension. */
 void izpi_host_tiles(int32_t size_x, int32_t size_y, int32_t* step_x, int32_t* step_y);
 
+/* grid.WalkGrid(sizeX, sizeY, PATTERN_SPIRAL) (internal/grid/grid.go:27-128): the order in which RendererImpl.Render queues its
+ * work units (renderer.go:151,172).  Start at the centre cell (sizeX/2, sizeY/2); at every step try the next direction of
+ * (up, right, down, left) and keep the previous one while the cell that way has been walked already; cells outside the grid
+ * are walked but not emitted.  xy receives size_x * size_y pairs {x, y}.  Pinned by the reference's own expected paths
+ * (grid_test.go:9-80). */
+void izpi_host_walk_grid_spiral(int32_t size_x, int32_t size_y, int32_t* xy);
+
 /* The claim policy of a shared tile cursor (izpi_render_tiles_shared): guided self-scheduling.  A claimer with room for
  * one more batch takes (tiles left) / (2 * takers) tiles, at most one full batch (batch_paths / tile_paths tiles) and at
  * least 2^20 paths' worth (smaller batches are launch-bound), with one atomic fetch-add on *cursor; takers = contexts x
@@ -48,9 +55,9 @@ void izpi_host_tiles(int32_t size_x, int32_t size_y, int32_t* step_x, int32_t* s
 int izpi_host_claim_tiles(uint64_t* cursor, int32_t n_tiles, int64_t tile_paths, int64_t batch_paths, int32_t takers,
                           int32_t* begin, int32_t* end);
 
-/* RendererImpl.Render (renderer.go:108-222) for the local path on one context: tile grid from
- * common.Tiles, tiles [tile_begin, tile_end) of the row-major grid submitted in batches, then
- * izpi_render_finish when `finish` is set.  tile_end = -1 means all tiles. */
+/* RendererImpl.Render (renderer.go:108-222) for the local path on one context (one GPU or a device group): tile grid from
+ * common.Tiles, queued in the reference's spiral order (izpi_host_walk_grid_spiral); the work units [tile_begin, tile_end)
+ * of that queue are submitted, then izpi_render_finish when `finish` is set.  tile_end = -1 means all of them. */
 int izpi_host_render(izpi_ctx* ctx, const izpi_render_config* cfg, int32_t tile_begin, int32_t tile_end,
                      int32_t finish, double* canvas_rgba, uint64_t* total_rays);
 

@@ -284,6 +284,28 @@ void izpi_host_tiles(int32_t sx, int32_t sy, int32_t* step_x, int32_t* step_y) {
   if (step_y) *step_y = ay;
 }
 
+void izpi_host_walk_grid_spiral(int32_t size_x, int32_t size_y, int32_t* xy) {
+  const int64_t total = (int64_t)size_x * size_y;
+  if (total <= 0 || !xy) return;
+  // walked cells, including the ring of cells just outside the grid that the spiral passes through: coordinates -1 .. size
+  const int64_t w = (int64_t)size_x + 2 * ((int64_t)(size_x > size_y ? size_x : size_y) + 2);
+  const int64_t off = (w - size_x) / 2;
+  std::vector<uint8_t> seen((size_t)(w * w), 0);
+  auto at = [&](int64_t x, int64_t y) -> uint8_t& { return seen[(size_t)((y + off) * w + (x + off))]; };
+  static const int dx[4] = {0, 1, 0, -1}, dy[4] = {-1, 0, 1, 0};  // up, right, down, left (grid.go:13-18)
+  int64_t x = size_x / 2, y = size_y / 2, n = 0, k = 0;
+  at(x, y) = 1;
+  xy[0] = (int32_t)x; xy[1] = (int32_t)y; n = 1;
+  while (n < total) {
+    const int d = (int)(k % 4);
+    if (at(x + dx[d], y + dy[d])) { k--; continue; }  // already walked: keep the previous direction (grid.go:66-69)
+    x += dx[d]; y += dy[d];
+    at(x, y) = 1;
+    if (x >= 0 && x < size_x && y >= 0 && y < size_y) { xy[2 * n] = (int32_t)x; xy[2 * n + 1] = (int32_t)y; n++; }
+    k++;
+  }
+}
+
 int izpi_host_claim_tiles(uint64_t* cursor, int32_t n_tiles, int64_t tile_paths, int64_t batch_paths, int32_t takers,
                           int32_t* begin, int32_t* end) {
   if (!cursor || !begin || !end || n_tiles <= 0) return 0;
@@ -324,10 +346,12 @@ int izpi_host_render(izpi_ctx* ctx, const izpi_render_config* cfg, int32_t tile_
   if (tile_begin < 0) tile_begin = 0;
   int rc = izpi_render_setup(ctx, cfg);
   if (rc != IZPI_OK) return rc;
+  std::vector<int32_t> walk((size_t)2 * total);
+  izpi_host_walk_grid_spiral(gx, gy, walk.data());  // the reference's queueing order (renderer.go:151)
   std::vector<uint32_t> tiles;
   tiles.reserve((size_t)4 * (tile_end > tile_begin ? tile_end - tile_begin : 0));
   for (int32_t t = tile_begin; t < tile_end; t++) {  // workUnit bounds, renderer.go:183-186
-    uint32_t tx = (uint32_t)(t % gx), ty = (uint32_t)(t / gx);
+    uint32_t tx = (uint32_t)walk[2 * (size_t)t], ty = (uint32_t)walk[2 * (size_t)t + 1];
     tiles.push_back(tx * sx); tiles.push_back(ty * sy);
     tiles.push_back(tx * sx + (sx - 1)); tiles.push_back(ty * sy + (sy - 1));
   }

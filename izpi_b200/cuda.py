@@ -54,7 +54,7 @@ EXPORTS = [
     "izpi_render_canvas_device", "izpi_render_finish", "izpi_debug_ray_aabb4", "izpi_debug_hit", "izpi_debug_fma_peak", "izpi_displace", "izpi_displace_fetch", "izpi_bvh4_build", "izpi_bvh4_build_fetch",
     "izpi_host_scene_create", "izpi_host_scene_destroy", "izpi_host_scene_num_nodes", "izpi_host_scene_bvh",
     "izpi_host_scene_num_lights", "izpi_host_scene_lights", "izpi_host_scene_desc", "izpi_host_scene_upload",
-    "izpi_host_tiles", "izpi_host_render", "izpi_host_claim_tiles",
+    "izpi_host_tiles", "izpi_host_render", "izpi_host_claim_tiles", "izpi_host_walk_grid_spiral",
     # include/izpi_proto.h
     "izpi_proto_scene_parse", "izpi_proto_scene_append_triangles", "izpi_proto_scene_to_scene", "izpi_proto_scene_spec",
     "izpi_proto_scene_name", "izpi_proto_scene_colour_representation", "izpi_proto_scene_total_triangles",
@@ -118,6 +118,8 @@ def lib():
     L.izpi_host_scene_upload.argtypes = [C.c_void_p, C.c_void_p]
     L.izpi_host_tiles.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.izpi_host_tiles.restype = None
+    L.izpi_host_walk_grid_spiral.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
+    L.izpi_host_walk_grid_spiral.restype = None
     L.izpi_host_claim_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.izpi_host_render.argtypes = [C.c_void_p, C.POINTER(RenderConfig), C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.POINTER(C.c_uint64)]

@@ -46,23 +46,9 @@ def walk_grid_spiral(size_x: int, size_y: int) -> np.ndarray:
     total = size_x * size_y
     if total <= 0:
         return np.zeros((0, 2), dtype=np.int32)
-    step = ((0, -1), (1, 0), (0, 1), (-1, 0))  # up, right, down, left
-    x, y = size_x // 2, size_y // 2
-    seen = {(x, y)}
-    path = [(x, y)]
-    k = 0
-    while len(path) < total:
-        dx, dy = step[k % 4]
-        nxt = (x + dx, y + dy)
-        if nxt in seen:
-            k -= 1
-            continue
-        x, y = nxt
-        seen.add(nxt)
-        if 0 <= x < size_x and 0 <= y < size_y:
-            path.append(nxt)
-        k += 1
-    return np.asarray(path, dtype=np.int32)
+    out = np.zeros((total, 2), dtype=np.int32)
+    cuda.lib().izpi_host_walk_grid_spiral(size_x, size_y, out.ctypes.data)  # csrc/host/host_scene.cpp
+    return out
 
 
 def spiral_tiles(size_x: int, size_y: int) -> np.ndarray:
