@@ -191,9 +191,19 @@ int izpi_host_scene_create(const izpi_scene_spec* spec, int threads, izpi_host_s
       s->bvh = NewBVH4(boxes, spec->bvh_seed, spec->bvh_rand_zero != 0, threads);  // transport.go:76
     }
     s->recs.resize(n); s->attrs.resize(n);
-    for (int i = 0; i < n; i++) {
-      int32_t src = s->bvh.perm[i];
-      s->recs[i] = recs[src]; s->attrs[i] = attrs[src]; rec_of[src] = i;
+    // world order = the BVH's leaf order: a 256-byte gather per primitive (2.9 GB for config 5), split over the host threads
+    // (perm is a permutation, so every thread writes its own slots)
+    auto permute = [&](int tid) {
+      for (int i = (int)((int64_t)n * tid / nt); i < (int)((int64_t)n * (tid + 1) / nt); i++) {
+        int32_t src = s->bvh.perm[i];
+        s->recs[i] = recs[src]; s->attrs[i] = attrs[src]; rec_of[src] = i;
+      }
+    };
+    {
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; t++) th.emplace_back(permute, t);
+      permute(0);
+      for (auto& t : th) t.join();
     }
   } else {
     s->recs.swap(recs); s->attrs.swap(attrs);
